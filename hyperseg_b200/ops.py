@@ -1,0 +1,239 @@
+"""Tensor-level wrappers over the C ABI (include/hsb200.h).
+
+PyTorch is used here only for device memory and the current stream: every function hands raw device
+pointers to libhsb200.so and returns a tensor it allocated for the output.  Inputs must live on a CUDA
+device -- there is no CPU implementation to fall back to, and none is attempted.
+
+Per-patch weight tensors are exchanged as logical ``(B, hp, fh, fw)`` tensors (the reference's shape).
+Their memory may be either contiguous NCHW (the reference layout) or "patch-major", i.e. what
+PyTorch calls channels_last -- ``(B, fh, fw, row)`` storage with ``row >= hp`` -- which is what
+:func:`signal2weights` produces and what the kernels stream without a layout change.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, HSB_BF16, HSB_F32, PAD_MODES, W_NCHW, W_PATCH_MAJOR
+
+ACTS = {"none": ACT_NONE, None: ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6}
+_DTYPES = {torch.float32: HSB_F32, torch.bfloat16: HSB_BF16}
+
+
+def _compute_dtype(x: torch.Tensor) -> torch.dtype:
+    if x.is_cuda and torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+    else:
+        dt = x.dtype
+    if dt not in _DTYPES:
+        raise TypeError(f"hyperseg_b200 kernels support float32 and bfloat16, got {dt}")
+    return dt
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "hyperseg_b200 operators run only on CUDA tensors (sm_100a kernels, no CPU fallback); "
+                f"got a tensor on {t.device}")
+
+
+def _require_inference(*tensors: torch.Tensor) -> None:
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "hyperseg_b200 implements the forward (inference) hot path only; backward kernels are not "
+            "built yet -- run under torch.no_grad() / model.eval()")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _fptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _affine(scale, shift, channels, device):
+    if scale is None and shift is None:
+        return None, None
+    if scale is None or shift is None:
+        raise ValueError("scale and shift must be given together")
+    scale = scale.to(device=device, dtype=torch.float32).contiguous()
+    shift = shift.to(device=device, dtype=torch.float32).contiguous()
+    if scale.numel() != channels or shift.numel() != channels:
+        raise ValueError(f"epilogue scale/shift must have {channels} entries")
+    return scale, shift
+
+
+def weight_layout(w: torch.Tensor):
+    """Classify a logical (B, hp, fh, fw) weight tensor -> (tensor, layout code, row stride)."""
+    if w.dim() != 4:
+        raise ValueError(f"per-patch weights must be 4-D (B, hp, fh, fw), got {tuple(w.shape)}")
+    B, hp, fh, fw = w.shape
+    st = w.stride()
+    if fw > 1:
+        row = st[3]
+    elif fh > 1:
+        row = st[2]
+    elif B > 1:
+        row = st[0]
+    else:
+        row = hp if (hp == 1 or st[1] == 1) else -1
+    ok = row >= hp
+    ok = ok and (hp == 1 or st[1] == 1)
+    ok = ok and (fw == 1 or st[3] == row)
+    ok = ok and (fh == 1 or st[2] == fw * row)
+    ok = ok and (B == 1 or st[0] == fh * fw * row)
+    if ok:
+        return w, W_PATCH_MAJOR, int(row)
+    if not w.is_contiguous():
+        w = w.contiguous()
+    return w, W_NCHW, 0
+
+
+def fold_bn(bn: torch.nn.BatchNorm2d):
+    """Eval-mode BatchNorm2d as y = scale * x + shift (fp32)."""
+    if bn.training or bn.running_mean is None:
+        raise NotImplementedError("only eval-mode BatchNorm with running statistics can be fused")
+    var = bn.running_var.float()
+    scale = torch.rsqrt(var + bn.eps)
+    if bn.weight is not None:
+        scale = scale * bn.weight.float()
+    shift = -bn.running_mean.float() * scale
+    if bn.bias is not None:
+        shift = shift + bn.bias.float()
+    return scale.contiguous(), shift.contiguous()
+
+
+def _prep_xw(x, w):
+    _require_cuda(x, w)
+    _require_inference(x, w)
+    dt = _compute_dtype(x)
+    x = x.to(dt).contiguous()
+    if w.dtype != dt:
+        w = w.to(dt)
+    w, layout, row = weight_layout(w)
+    if x.shape[0] != w.shape[0]:
+        raise ValueError(f"batch mismatch between x {tuple(x.shape)} and weights {tuple(w.shape)}")
+    return x, w, layout, row, dt
+
+
+def patch_conv1x1(x, w, out_channels, groups=1, scale=None, shift=None, act="none"):
+    """Patch-wise 1x1 convolution (+ fused per-channel affine and activation)."""
+    x, w, layout, row, dt = _prep_xw(x, w)
+    B, Cin, H, W = x.shape
+    hp = out_channels * (Cin // groups)
+    if w.shape[1] != hp:
+        raise ValueError(f"expected {hp} weights per patch, got {w.shape[1]}")
+    fh, fw = w.shape[-2:]
+    scale, shift = _affine(scale, shift, out_channels, x.device)
+    y = torch.empty((B, out_channels, H, W), dtype=dt, device=x.device)
+    _lib.check(_lib.load().hsb_patch_conv1x1_fwd(
+        x.data_ptr(), w.data_ptr(), y.data_ptr(), _fptr(scale), _fptr(shift), ACTS[act],
+        B, Cin, out_channels, H, W, fh, fw, groups, _DTYPES[dt], layout, row, _stream()), "hsb_patch_conv1x1_fwd")
+    return y
+
+
+def patch_ir(x, w, hidden, out_channels, bn1, bn2, bn3, residual=False):
+    """Fused patch-wise inverted residual block; bn* are (scale, shift) pairs of the folded BatchNorms."""
+    x, w, layout, row, dt = _prep_xw(x, w)
+    B, Cin, H, W = x.shape
+    hp = Cin * hidden + 9 * hidden + hidden * out_channels
+    if w.shape[1] != hp:
+        raise ValueError(f"expected {hp} weights per patch, got {w.shape[1]}")
+    fh, fw = w.shape[-2:]
+    s1, b1 = _affine(bn1[0], bn1[1], hidden, x.device)
+    s2, b2 = _affine(bn2[0], bn2[1], hidden, x.device)
+    s3, b3 = _affine(bn3[0], bn3[1], out_channels, x.device)
+    y = torch.empty((B, out_channels, H, W), dtype=dt, device=x.device)
+    _lib.check(_lib.load().hsb_patch_ir_fwd(
+        x.data_ptr(), w.data_ptr(), y.data_ptr(), s1.data_ptr(), b1.data_ptr(), s2.data_ptr(), b2.data_ptr(),
+        s3.data_ptr(), b3.data_ptr(), B, Cin, hidden, out_channels, H, W, fh, fw, int(bool(residual)),
+        _DTYPES[dt], layout, row, _stream()), "hsb_patch_ir_fwd")
+    return y
+
+
+def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
+    """Grouped 1x1 head: signal (B, C, fh, fw) -> logical (B, hp, fh, fw) weights in patch-major storage.
+
+    ``ws`` is the nn.Conv2d weight (out_ch, sig_ch/groups, 1, 1); only the first ``hp`` output channels
+    are produced (the reference computes all ``out_ch`` and slices)."""
+    _require_cuda(s, ws)
+    _require_inference(s, ws)
+    dt = _compute_dtype(s)
+    if s.dtype != dt:
+        s = s.to(dt)
+    ws = ws.detach().to(dt).reshape(ws.shape[0], -1).contiguous()
+    B, C, fh, fw = s.shape
+    out_ch = ws.shape[0]
+    if ws.shape[1] * groups != sig_ch:
+        raise ValueError("signal2weights weight does not match sig_ch / groups")
+    if sig_index + sig_ch > C:
+        raise ValueError(f"signal slice [{sig_index}, {sig_index + sig_ch}) exceeds {C} signal channels")
+    st = s.stride()
+    if fh > 1 and fw > 1 and st[2] != fw * st[3]:
+        s = s.contiguous()
+        st = s.stride()
+    sp = st[3] if fw > 1 else (st[2] if fh > 1 else 1)
+    row = (hp + 7) // 8 * 8
+    buf = torch.empty((B, fh, fw, row), dtype=dt, device=s.device)
+    _lib.check(_lib.load().hsb_signal2weights_fwd(
+        s.data_ptr(), ws.data_ptr(), buf.data_ptr(), B, sig_index, sig_ch, out_ch, hp, groups, fh, fw,
+        st[0], st[1], sp, _DTYPES[dt], W_PATCH_MAJOR, row, _stream()), "hsb_signal2weights_fwd")
+    return buf[..., :hp].permute(0, 3, 1, 2)
+
+
+def patch_conv(x, w, out_channels, kernel_size, padding, dilation=(1, 1), groups=1, padding_mode="reflect",
+               scale=None, shift=None, act="none"):
+    """General patch-wise convolution (MetaPatchConv2d / HyperPatchConv2d semantics)."""
+    x, w, layout, row, dt = _prep_xw(x, w)
+    B, Cin, H, W = x.shape
+    kh, kw = kernel_size
+    hp = out_channels * (Cin // groups) * kh * kw
+    if w.shape[1] != hp:
+        raise ValueError(f"expected {hp} weights per patch, got {w.shape[1]}")
+    fh, fw = w.shape[-2:]
+    scale, shift = _affine(scale, shift, out_channels, x.device)
+    y = torch.empty((B, out_channels, H, W), dtype=dt, device=x.device)
+    _lib.check(_lib.load().hsb_patch_conv_fwd(
+        x.data_ptr(), w.data_ptr(), y.data_ptr(), _fptr(scale), _fptr(shift), ACTS[act],
+        B, Cin, out_channels, H, W, fh, fw, kh, kw, padding[0], padding[1], dilation[0], dilation[1], groups,
+        PAD_MODES[padding_mode], _DTYPES[dt], layout, row, _stream()), "hsb_patch_conv_fwd")
+    return y
+
+
+def meta_conv2d(x, w, out_channels, kernel_size, padding=(0, 0), dilation=(1, 1), groups=1,
+                padding_mode="zeros"):
+    """Per-sample dynamic convolution, stride 1 (MetaConv2d semantics); w is (N, hyper_params)."""
+    _require_cuda(x, w)
+    _require_inference(x, w)
+    dt = _compute_dtype(x)
+    x = x.to(dt).contiguous()
+    w = w.to(dt).reshape(w.shape[0], -1).contiguous()
+    N, Cin, H, W = x.shape
+    kh, kw = kernel_size
+    if w.shape[0] != N or w.shape[1] != out_channels * (Cin // groups) * kh * kw:
+        raise ValueError(f"weights {tuple(w.shape)} do not match input {tuple(x.shape)}")
+    Ho = H + 2 * padding[0] - dilation[0] * (kh - 1)
+    Wo = W + 2 * padding[1] - dilation[1] * (kw - 1)
+    y = torch.empty((N, out_channels, Ho, Wo), dtype=dt, device=x.device)
+    _lib.check(_lib.load().hsb_meta_conv2d_fwd(
+        x.data_ptr(), w.data_ptr(), y.data_ptr(), N, Cin, out_channels, H, W, kh, kw,
+        padding[0], padding[1], dilation[0], dilation[1], groups, PAD_MODES[padding_mode], _DTYPES[dt],
+        _stream()), "hsb_meta_conv2d_fwd")
+    return y
+
+
+def weights_to_patch_major(w):
+    """(B, hp, fh, fw) contiguous -> same logical tensor in patch-major storage."""
+    _require_cuda(w)
+    if w.dtype not in _DTYPES:
+        raise TypeError(f"unsupported dtype {w.dtype}")
+    w = w.contiguous()
+    B, hp, fh, fw = w.shape
+    row = (hp + 7) // 8 * 8
+    buf = torch.empty((B, fh, fw, row), dtype=w.dtype, device=w.device)
+    _lib.check(_lib.load().hsb_weights_to_patch_major(
+        w.data_ptr(), buf.data_ptr(), B, hp, fh, fw, row, _DTYPES[w.dtype], _stream()),
+        "hsb_weights_to_patch_major")
+    return buf[..., :hp].permute(0, 3, 1, 2)

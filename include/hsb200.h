@@ -1,0 +1,148 @@
+/*
+ * hsb200.h -- C ABI of libhsb200.so: the B200 (sm_100a) implementation of HyperSeg's
+ * decoder hot path (per-patch dynamic convolutions + the signal->weights heads).
+ *
+ * The reference (YuvalNirkin/hyperseg) has no FFI of its own: its hot path is Python
+ * calling ATen.  Each entry point below therefore names the reference Python function
+ * whose arithmetic it replaces (paths relative to the reference repo root).  The host
+ * side (hyperseg_b200/nn/*.py) keeps the reference's nn.Module surface and calls these
+ * through ctypes; see INTEGRATION.md for the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a raw CUDA device pointer owned by the caller (inputs, outputs,
+ *     workspace); the library allocates nothing and keeps no state between calls.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises.
+ *   - return value: 0 on success, a negative hsb_status otherwise; the text of the last
+ *     failure on the calling thread is available from hsb_last_error().
+ *   - there is no CPU path: a NULL/host pointer or a missing device is an error.
+ *   - feature maps are NCHW, contiguous.  `dtype` applies to x, w and y alike
+ *     (accumulation is always fp32).
+ *   - per-patch weight tensors come in one of two layouts (hsb_wlayout):
+ *       HSB_W_NCHW         the reference layout (B, hp, fh, fw), contiguous
+ *       HSB_W_PATCH_MAJOR  (B, fh, fw, row) with `w_row_stride` elements between
+ *                          consecutive patches (>= hp); this is what
+ *                          hsb_signal2weights_fwd emits and what torch calls
+ *                          channels_last for a (B, hp, fh, fw) tensor.
+ *     Patch (b, i, j) is patch index p = (b*fh + i)*fw + j.
+ */
+#ifndef HSB200_H_
+#define HSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSB200_VERSION 100 /* major*100 + minor */
+
+typedef enum hsb_status {
+    HSB_OK = 0,
+    HSB_ERR_INVALID_ARG = -1,  /* bad shape / null pointer / misaligned buffer          */
+    HSB_ERR_UNSUPPORTED = -2,  /* legal in the reference but not implemented by kernels */
+    HSB_ERR_CUDA = -3,         /* a CUDA runtime call or launch failed                  */
+    HSB_ERR_NO_DEVICE = -4     /* no sm_100 device visible                              */
+} hsb_status;
+
+typedef enum hsb_dtype { HSB_F32 = 0, HSB_BF16 = 1 } hsb_dtype;
+typedef enum hsb_act { HSB_ACT_NONE = 0, HSB_ACT_RELU = 1, HSB_ACT_RELU6 = 2 } hsb_act;
+typedef enum hsb_wlayout { HSB_W_NCHW = 0, HSB_W_PATCH_MAJOR = 1 } hsb_wlayout;
+typedef enum hsb_padmode { HSB_PAD_ZEROS = 0, HSB_PAD_REFLECT = 1, HSB_PAD_REPLICATE = 2,
+                           HSB_PAD_CIRCULAR = 3 } hsb_padmode;
+
+/* Library / build introspection. */
+int hsb_version(void);
+const char* hsb_last_error(void);
+/* Writes the number of SMs and the compute capability (major*10+minor) of the current
+ * device; HSB_ERR_NO_DEVICE when there is none. */
+int hsb_device_info(int* sm_count, int* compute_capability);
+
+/*
+ * Patch-wise 1x1 convolution with a fused per-channel affine + activation epilogue.
+ *   y[b,o,i*ph+u,j*pw+v] = act( post_scale[o] * sum_c Wm[o,c] * x[b, g*Cin/G + c, ...] + post_shift[o] )
+ *   Wm[o,c] = w_patch[o*(Cin/G) + c],  g = o / (Cout/G),  ph = H/fh, pw = W/fw.
+ * Replaces HyperPatchNoPadding.forward (hyperseg/models/hyperseg_v1_0.py:486-498,
+ * hyperseg_v1_0_unify.py:483-494) and, through post_scale/post_shift/act, the eval-mode
+ * BatchNorm2d + ReLU that make_hyper_patch_conv2d_block appends (hyperseg_v1_0.py:753-756).
+ * post_scale/post_shift may both be NULL (identity epilogue).  H%fh==0 and W%fw==0.
+ */
+int hsb_patch_conv1x1_fwd(const void* x, const void* w, void* y,
+                          const float* post_scale, const float* post_shift, int act,
+                          int B, int Cin, int Cout, int H, int W, int fh, int fw, int groups,
+                          int dtype, int w_layout, int64_t w_row_stride, void* stream);
+
+/*
+ * Fused patch-wise inverted-residual MetaBlock (v1_0 / unify semantics: tile-local halo).
+ *   tile = reflect_pad(x,1)[b, :, i*ph : i*ph+ph+2, j*pw : j*pw+pw+2]
+ *   h = relu6(bn1(W1 . tile));  d = relu6(bn2(dw3x3_valid(h; W2)));  o = bn3(W3 . d)
+ *   y[b,:,i*ph+u,j*pw+v] = o[:,u,v] (+ x when `residual`)
+ *   per-patch weight vector = [W1 (hid x Cin) | W2 (hid x 3 x 3) | W3 (Cout x hid)].
+ * Replaces HyperPatchInvertedResidual.conv/forward (hyperseg/models/hyperseg_v1_0.py:328-376,
+ * hyperseg_v1_0_unify.py:342-389).  bn*_scale/shift are the eval-mode BatchNorm folded to
+ * y = scale*x + shift (scale = gamma/sqrt(var+eps), shift = beta - mean*scale), fp32,
+ * lengths hid, hid, Cout.
+ */
+int hsb_patch_ir_fwd(const void* x, const void* w, void* y,
+                     const float* bn1_scale, const float* bn1_shift,
+                     const float* bn2_scale, const float* bn2_shift,
+                     const float* bn3_scale, const float* bn3_shift,
+                     int B, int Cin, int hid, int Cout, int H, int W, int fh, int fw,
+                     int residual, int dtype, int w_layout, int64_t w_row_stride, void* stream);
+
+/*
+ * Weight head: grouped 1x1 convolution from the signal map to per-patch weights.
+ *   Wout[b, o, i, j] = sum_{k < sig_ch/G} Ws[o,k] * s[b, sig_index + (o / (out_ch/G))*(sig_ch/G) + k, i, j],  o < hp
+ * Replaces apply_signal2weights + nn.Conv2d(groups) (hyperseg/models/hyperseg_v1_0.py:315-326,
+ * :473-484, :531-541), WeightLayer.forward (hyperseg_v1_0_unify.py:287-309) and one head of
+ * Conv2dMulti (hyperseg_v0_1.py:336-362).
+ *   s   (B, *, fh, fw) signal with element strides s_stride_b / s_stride_c / s_stride_p
+ *       (NCHW: C*fh*fw, fh*fw, 1;  NHWC: fh*fw*C, 1, C)
+ *   ws  (out_ch, sig_ch/G) contiguous, same dtype (the nn.Conv2d weight, out_ch a multiple of G)
+ *   w_out in `out_layout`; rows of HSB_W_PATCH_MAJOR are `out_row_stride` elements apart and
+ *       only the first hp entries of each row are written.
+ */
+int hsb_signal2weights_fwd(const void* s, const void* ws, void* w_out,
+                           int B, int sig_index, int sig_ch, int out_ch, int hp, int groups,
+                           int fh, int fw,
+                           int64_t s_stride_b, int64_t s_stride_c, int64_t s_stride_p,
+                           int dtype, int out_layout, int64_t out_row_stride, void* stream);
+
+/*
+ * General patch-wise convolution (any kernel size / groups / dilation, stride 1):
+ *   tile = pad(x, (pad_h,pad_w), pad_mode)[b, :, i*ph : i*ph+ph+2*pad_h, j*pw : j*pw+pw+2*pad_w]
+ *   y patch = valid_conv(tile, Wm),  Wm[o,c,ky,kx] = w_patch[((o*(Cin/G)+c)*kh+ky)*kw+kx]
+ * Requires 2*pad == dilation*(k-1) per axis (output patch == input patch, as every
+ * reference call site has).  Replaces MetaPatch.forward + MetaConv2d.forward
+ * (hyperseg/models/layers/meta_patch.py:35-57, meta_conv.py:163-186) and HyperPatch.forward
+ * (hyperseg/models/hyperseg_v1_0.py:543-557).  Same fused epilogue as the 1x1 entry point.
+ */
+int hsb_patch_conv_fwd(const void* x, const void* w, void* y,
+                       const float* post_scale, const float* post_shift, int act,
+                       int B, int Cin, int Cout, int H, int W, int fh, int fw,
+                       int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, int groups,
+                       int pad_mode, int dtype, int w_layout, int64_t w_row_stride, void* stream);
+
+/*
+ * Per-batch-element dynamic convolution, stride 1, explicit padding:
+ *   y[n] = conv2d(pad(x[n]), Wm[n]),  w is (N, Cout*Cin/G*kh*kw) contiguous.
+ * Replaces MetaConv2d.forward used on its own (hyperseg/models/layers/meta_conv.py:163-186).
+ */
+int hsb_meta_conv2d_fwd(const void* x, const void* w, void* y,
+                        int N, int Cin, int Cout, int H, int W,
+                        int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, int groups,
+                        int pad_mode, int dtype, void* stream);
+
+/*
+ * Layout change (B, hp, fh, fw) -> (B, fh, fw, row_stride) for weights handed over in the
+ * reference layout.  Replaces weight.permute(0,2,3,1).reshape(...) at
+ * hyperseg/models/hyperseg_v1_0.py:345-347, :492-493, :549.
+ */
+int hsb_weights_to_patch_major(const void* w_nchw, void* w_pm, int B, int hp, int fh, int fw,
+                               int64_t row_stride, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSB200_H_ */
