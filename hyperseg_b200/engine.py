@@ -1,0 +1,137 @@
+"""Inference engine: the call a user makes to segment frames on one GPU.
+
+    engine = SegmentationEngine(model, batch=8, height=512, width=1024)      # bf16, CUDA-graph captured
+    labels = engine(frames)          # frames: pinned host float32 (B,3,H,W) -> pinned host uint8 (B,H,W)
+
+What it adds around the nn.Module mirror:
+  * the stock-PyTorch parts (EfficientNet encoder, weight-mapper trunk) are put in inference form on a private
+    copy of the model: eval-mode BatchNorms folded into the preceding convolutions, parameters cast to the
+    compute dtype once (instead of autocast re-casting them every call);
+  * the whole forward -- stock convolutions, decoder glue and the libhsb200 kernels -- is captured in one CUDA
+    graph, so a step is one graph launch (the decoder alone is ~25 small launches per frame batch);
+  * host<->device transfers use pinned staging buffers and the engine's stream.
+The model handed in is not modified, and outputs equal model(frames) up to rounding.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> None:
+    scale, shift = ops.fold_bn(bn)
+    w = conv.weight.detach().float() * scale.view(-1, 1, 1, 1).to(conv.weight.device)
+    b = shift.to(conv.weight.device)
+    if conv.bias is not None:
+        b = b + conv.bias.detach().float() * scale.to(conv.weight.device)
+    conv.weight = nn.Parameter(w.to(conv.weight.dtype), requires_grad=False)
+    conv.bias = nn.Parameter(b.to(conv.weight.dtype), requires_grad=False)
+
+
+def fold_static_batchnorms(model: nn.Module) -> int:
+    """Fold eval-mode BatchNorm2d into the static convolution that feeds it, in the encoder and the weight mapper.
+
+    The decoder's BatchNorms belong to the dynamic layers and are fused inside the CUDA kernels instead."""
+    from .nn.efficientnet import EfficientNet, MBConvBlock
+    folded = 0
+
+    def fold(owner, conv_name, bn_name):
+        nonlocal folded
+        conv, bn = getattr(owner, conv_name, None), getattr(owner, bn_name, None)
+        if isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d) and not bn.training:
+            _fold_conv_bn(conv, bn)
+            setattr(owner, bn_name, nn.Identity())
+            folded += 1
+
+    for root_name in ("backbone", "weight_mapper"):
+        root = getattr(model, root_name, None)
+        if root is None:
+            continue
+        for m in root.modules():
+            if isinstance(m, EfficientNet):
+                fold(m, "_conv_stem", "_bn0")
+                fold(m, "_conv_head", "_bn1")
+            elif isinstance(m, MBConvBlock):
+                fold(m, "_expand_conv", "_bn0")
+                fold(m, "_depthwise_conv", "_bn1")
+                fold(m, "_project_conv", "_bn2")
+            elif isinstance(m, nn.Sequential):
+                names = [n for n, _ in m.named_children()]
+                for a, b in zip(names, names[1:]):
+                    fold(m, a, b)
+    return folded
+
+
+class SegmentationEngine:
+    def __init__(self, model: nn.Module, batch: int, height: int, width: int, device="cuda",
+                 dtype=torch.bfloat16, use_graph: bool = True, fold_bn: bool = True, warmup: int = 3):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.shape = (batch, 3, height, width)
+        net = copy.deepcopy(model).eval()
+        for p in net.parameters():
+            p.requires_grad_(False)
+        self.folded = fold_static_batchnorms(net) if fold_bn else 0
+        # the decoder's BatchNorms are fused into the CUDA kernels: fold them once, in fp32, before the cast
+        pinned = []
+        for m in net.decoder.modules():
+            if isinstance(m, nn.BatchNorm2d) and m.running_mean is not None:
+                pinned.append((m, ops.fold_bn(m)))
+        self.net = net.to(self.device, dtype)
+        for m, (scale, shift) in pinned:
+            m._hsb_folded = (scale.to(self.device, torch.float32).contiguous(),
+                             shift.to(self.device, torch.float32).contiguous())
+        self.stream = torch.cuda.Stream(self.device)
+        self.frames_dev = torch.zeros(self.shape, device=self.device, dtype=torch.float32)
+        self.host_out = torch.empty((batch, height, width), dtype=torch.uint8).pin_memory()
+        self.logits = None
+        self.labels = None
+        self.graph = None
+        self.launches_per_step = 0
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            for _ in range(max(1, warmup)):
+                self._forward_static()
+            self.stream.synchronize()
+            before = ops.launch_count()
+            self._forward_static()
+            self.launches_per_step = ops.launch_count() - before
+            if use_graph:
+                self.stream.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=self.stream):
+                    self._forward_static()
+                self.graph = graph
+        self.stream.synchronize()
+
+    def _forward_static(self):
+        x = self.frames_dev.to(self.dtype)
+        self.logits = self.net(x)
+        self.labels = self.logits.argmax(1).to(torch.uint8)
+
+    @torch.no_grad()
+    def step(self):
+        """One forward over the frames currently in ``frames_dev`` (enqueued on the engine's stream)."""
+        with torch.cuda.stream(self.stream):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._forward_static()
+
+    @torch.no_grad()
+    def __call__(self, frames: torch.Tensor) -> torch.Tensor:
+        """Host frames (pinned float32, B x 3 x H x W) -> host labels (pinned uint8, B x H x W)."""
+        if tuple(frames.shape) != self.shape:
+            raise ValueError(f"engine was built for frames of shape {self.shape}, got {tuple(frames.shape)}")
+        with torch.cuda.stream(self.stream):
+            self.frames_dev.copy_(frames, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._forward_static()
+            self.host_out.copy_(self.labels, non_blocking=True)
+        self.stream.synchronize()
+        return self.host_out

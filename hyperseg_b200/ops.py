@@ -16,6 +16,19 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, HSB_BF16, HSB_F32, PAD_MODES, W_NCHW, W_PATCH_MAJOR
 
+_LAUNCHES = 0      # kernels launched through the C ABI by this process (each entry point launches exactly one)
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def _call(fn_name, *args):
+    global _LAUNCHES
+    _lib.check(getattr(_lib.load(), fn_name)(*args), fn_name)
+    _LAUNCHES += 1
+
+
 ACTS = {"none": ACT_NONE, None: ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6}
 _DTYPES = {torch.float32: HSB_F32, torch.bfloat16: HSB_BF16}
 
@@ -92,7 +105,13 @@ def weight_layout(w: torch.Tensor):
 
 
 def fold_bn(bn: torch.nn.BatchNorm2d):
-    """Eval-mode BatchNorm2d as y = scale * x + shift (fp32)."""
+    """Eval-mode BatchNorm2d as y = scale * x + shift (fp32).
+
+    An inference engine may pin the result on the module (``_hsb_folded``) so that it is computed once, in fp32,
+    before the module's buffers are cast to a 16-bit dtype."""
+    cached = getattr(bn, "_hsb_folded", None)
+    if cached is not None:
+        return cached
     if bn.training or bn.running_mean is None:
         raise NotImplementedError("only eval-mode BatchNorm with running statistics can be fused")
     var = bn.running_var.float()
@@ -128,9 +147,8 @@ def patch_conv1x1(x, w, out_channels, groups=1, scale=None, shift=None, act="non
     fh, fw = w.shape[-2:]
     scale, shift = _affine(scale, shift, out_channels, x.device)
     y = torch.empty((B, out_channels, H, W), dtype=dt, device=x.device)
-    _lib.check(_lib.load().hsb_patch_conv1x1_fwd(
-        x.data_ptr(), w.data_ptr(), y.data_ptr(), _fptr(scale), _fptr(shift), ACTS[act],
-        B, Cin, out_channels, H, W, fh, fw, groups, _DTYPES[dt], layout, row, _stream()), "hsb_patch_conv1x1_fwd")
+    _call("hsb_patch_conv1x1_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), _fptr(scale), _fptr(shift), ACTS[act],
+        B, Cin, out_channels, H, W, fh, fw, groups, _DTYPES[dt], layout, row, _stream())
     return y
 
 
@@ -146,10 +164,9 @@ def patch_ir(x, w, hidden, out_channels, bn1, bn2, bn3, residual=False):
     s2, b2 = _affine(bn2[0], bn2[1], hidden, x.device)
     s3, b3 = _affine(bn3[0], bn3[1], out_channels, x.device)
     y = torch.empty((B, out_channels, H, W), dtype=dt, device=x.device)
-    _lib.check(_lib.load().hsb_patch_ir_fwd(
-        x.data_ptr(), w.data_ptr(), y.data_ptr(), s1.data_ptr(), b1.data_ptr(), s2.data_ptr(), b2.data_ptr(),
+    _call("hsb_patch_ir_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), s1.data_ptr(), b1.data_ptr(), s2.data_ptr(), b2.data_ptr(),
         s3.data_ptr(), b3.data_ptr(), B, Cin, hidden, out_channels, H, W, fh, fw, int(bool(residual)),
-        _DTYPES[dt], layout, row, _stream()), "hsb_patch_ir_fwd")
+        _DTYPES[dt], layout, row, _stream())
     return y
 
 
@@ -177,9 +194,8 @@ def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
     sp = st[3] if fw > 1 else (st[2] if fh > 1 else 1)
     row = (hp + 7) // 8 * 8
     buf = torch.empty((B, fh, fw, row), dtype=dt, device=s.device)
-    _lib.check(_lib.load().hsb_signal2weights_fwd(
-        s.data_ptr(), ws.data_ptr(), buf.data_ptr(), B, sig_index, sig_ch, out_ch, hp, groups, fh, fw,
-        st[0], st[1], sp, _DTYPES[dt], W_PATCH_MAJOR, row, _stream()), "hsb_signal2weights_fwd")
+    _call("hsb_signal2weights_fwd", s.data_ptr(), ws.data_ptr(), buf.data_ptr(), B, sig_index, sig_ch, out_ch, hp, groups, fh, fw,
+        st[0], st[1], sp, _DTYPES[dt], W_PATCH_MAJOR, row, _stream())
     return buf[..., :hp].permute(0, 3, 1, 2)
 
 
@@ -195,10 +211,9 @@ def patch_conv(x, w, out_channels, kernel_size, padding, dilation=(1, 1), groups
     fh, fw = w.shape[-2:]
     scale, shift = _affine(scale, shift, out_channels, x.device)
     y = torch.empty((B, out_channels, H, W), dtype=dt, device=x.device)
-    _lib.check(_lib.load().hsb_patch_conv_fwd(
-        x.data_ptr(), w.data_ptr(), y.data_ptr(), _fptr(scale), _fptr(shift), ACTS[act],
+    _call("hsb_patch_conv_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), _fptr(scale), _fptr(shift), ACTS[act],
         B, Cin, out_channels, H, W, fh, fw, kh, kw, padding[0], padding[1], dilation[0], dilation[1], groups,
-        PAD_MODES[padding_mode], _DTYPES[dt], layout, row, _stream()), "hsb_patch_conv_fwd")
+        PAD_MODES[padding_mode], _DTYPES[dt], layout, row, _stream())
     return y
 
 
@@ -217,10 +232,9 @@ def meta_conv2d(x, w, out_channels, kernel_size, padding=(0, 0), dilation=(1, 1)
     Ho = H + 2 * padding[0] - dilation[0] * (kh - 1)
     Wo = W + 2 * padding[1] - dilation[1] * (kw - 1)
     y = torch.empty((N, out_channels, Ho, Wo), dtype=dt, device=x.device)
-    _lib.check(_lib.load().hsb_meta_conv2d_fwd(
-        x.data_ptr(), w.data_ptr(), y.data_ptr(), N, Cin, out_channels, H, W, kh, kw,
+    _call("hsb_meta_conv2d_fwd", x.data_ptr(), w.data_ptr(), y.data_ptr(), N, Cin, out_channels, H, W, kh, kw,
         padding[0], padding[1], dilation[0], dilation[1], groups, PAD_MODES[padding_mode], _DTYPES[dt],
-        _stream()), "hsb_meta_conv2d_fwd")
+        _stream())
     return y
 
 
@@ -233,7 +247,5 @@ def weights_to_patch_major(w):
     B, hp, fh, fw = w.shape
     row = (hp + 7) // 8 * 8
     buf = torch.empty((B, fh, fw, row), dtype=w.dtype, device=w.device)
-    _lib.check(_lib.load().hsb_weights_to_patch_major(
-        w.data_ptr(), buf.data_ptr(), B, hp, fh, fw, row, _DTYPES[w.dtype], _stream()),
-        "hsb_weights_to_patch_major")
+    _call("hsb_weights_to_patch_major", w.data_ptr(), buf.data_ptr(), B, hp, fh, fw, row, _DTYPES[w.dtype], _stream())
     return buf[..., :hp].permute(0, 3, 1, 2)

@@ -1,0 +1,255 @@
+"""Parity of the CUDA kernels (through the C ABI) with the reference -- run on the B200 with -m gpu.
+
+Three kinds of evidence:
+  * the committed golden vectors (outputs of the unmodified reference, tests/golden/ops.npz) in fp32;
+  * the oracle on seeded inputs at shapes the oracle finishes in seconds, incl. the exact per-level shapes of
+    HyperSeg-M at 512x1024 (one image), in fp32 and bf16, for every weight layout the ABI accepts;
+  * size-independent properties at BASELINE.json's full size (batch 8): patch locality, batch independence,
+    linearity in the weights, agreement between independent kernels.
+Tolerances (relative to max |reference|): fp32 2e-5 (north_star allows 1e-3); bf16 I/O 1.5e-2 against the
+float64 oracle evaluated on the same bf16-rounded inputs.
+"""
+import pytest
+import torch
+
+import cases
+from conftest import mirror_namespace, rel_err
+from hyperseg_b200 import ops
+from hyperseg_b200.synthetic import deterministic_init
+from oracle import hyperseg_oracle as orc
+
+pytestmark = pytest.mark.gpu
+F32_TOL = 2e-5
+BF16_TOL = 1.5e-2
+DEV = "cuda"
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def _bn(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, generator=g) + 0.5, torch.randn(n, generator=g) * 0.1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# golden vectors (reference outputs), fp32
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(cases.OP_CASES))
+def test_golden_op_case_fp32(name, golden_ops):
+    case = cases.OP_CASES[name]
+    m = cases.build_op_module(mirror_namespace(), case)
+    deterministic_init(m, cases.case_seed(name)).eval().to(DEV)
+    x = torch.from_numpy(golden_ops[f"{name}/x"]).to(DEV)
+    w = torch.from_numpy(golden_ops[f"{name}/w"]).to(DEV)
+    with torch.no_grad():
+        y = m(x, w)
+    ref = torch.from_numpy(golden_ops[f"{name}/y"])
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert rel_err(y.cpu(), ref) < F32_TOL
+
+
+@pytest.mark.parametrize("name", sorted(cases.HEAD_CASES))
+def test_golden_head_fp32(name, golden_ops):
+    from hyperseg_b200.nn.hyperseg_v1_0 import HyperPatchNoPadding
+    c = cases.HEAD_CASES[name]
+    layer = HyperPatchNoPadding(c["hp"], 1, 1)
+    layer.init_signal2weights(c["sc"], c["idx"], c["groups"])
+    deterministic_init(layer, cases.case_seed(name)).to(DEV)
+    s = torch.from_numpy(golden_ops[f"{name}/s"]).to(DEV)
+    with torch.no_grad():
+        w = layer.apply_signal2weights(s)
+    assert w.shape == golden_ops[f"{name}/y"].shape
+    assert w.stride(1) == 1, "heads must emit patch-major rows"
+    assert rel_err(w.cpu(), golden_ops[f"{name}/y"]) < F32_TOL
+
+
+@pytest.mark.parametrize("name", ["ir_L4", "ir_small", "nopad_p4", "block1x1", "mpblock_dw", "v01_ir"])
+def test_golden_op_case_bf16(name, golden_ops):
+    """bf16 I/O against the reference's fp32 answer: error budget = bf16 rounding of inputs and outputs."""
+    case = cases.OP_CASES[name]
+    m = cases.build_op_module(mirror_namespace(), case)
+    deterministic_init(m, cases.case_seed(name)).eval().to(DEV)
+    x = torch.from_numpy(golden_ops[f"{name}/x"]).to(DEV).bfloat16()
+    w = torch.from_numpy(golden_ops[f"{name}/w"]).to(DEV).bfloat16()
+    with torch.no_grad():
+        y = m(x, w)
+    assert y.dtype == torch.bfloat16
+    assert rel_err(y.float().cpu(), golden_ops[f"{name}/y"]) < 3e-2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle on seeded inputs: HyperSeg-M level shapes (one image), every layout, fp32 + bf16
+# ---------------------------------------------------------------------------------------------------------
+M_1X1 = {"L0": (82, 64, 16, 32), "L1": (94, 32, 32, 64), "L2": (44, 16, 64, 128)}      # Cin, Cout, H, W (fh,fw = 16,32)
+M_IR = {"L3": (24, 48, 16, 128, 256), "L4": (34, 68, 19, 256, 512)}                    # Cin, hid, Cout, H, W
+
+
+def _layouts(w):
+    """The same logical weights in the three storage forms the ABI accepts."""
+    pm = ops.weights_to_patch_major(w)
+    B, hp, fh, fw = w.shape
+    wide = torch.zeros(B, fh, fw, hp + 24, device=w.device, dtype=w.dtype)
+    wide[..., 5:5 + hp] = w.permute(0, 2, 3, 1)
+    sliced = wide[..., 5:5 + hp].permute(0, 3, 1, 2)       # unaligned start, row stride > hp (unify-style slice)
+    return {"nchw": w, "patch_major": pm, "sliced": sliced}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("level", sorted(M_1X1))
+def test_conv1x1_hyperseg_m_levels(level, dtype):
+    Cin, Cout, H, W = M_1X1[level]
+    x = _rand((1, Cin, H, W), 1).to(DEV, dtype)
+    w = _rand((1, Cin * Cout, 16, 32), 2, 0.3).to(DEV, dtype)
+    scale, shift = _bn(Cout, 3)
+    ref = orc.patch_conv1x1(x.float().cpu(), w.float().cpu(), Cout, 1, scale, shift, "relu")
+    tol = F32_TOL if dtype == torch.float32 else BF16_TOL
+    for lname, wl in _layouts(w).items():
+        y = ops.patch_conv1x1(x, wl, Cout, 1, scale.to(DEV), shift.to(DEV), "relu")
+        assert rel_err(y.float().cpu(), ref) < tol, lname
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("level", sorted(M_IR))
+def test_ir_hyperseg_m_levels(level, dtype):
+    Cin, hid, Cout, H, W = M_IR[level]
+    hp = Cin * hid + 9 * hid + hid * Cout
+    x = _rand((1, Cin, H, W), 4).to(DEV, dtype)
+    w = _rand((1, hp, 16, 32), 5, 0.3).to(DEV, dtype)
+    bns = [_bn(hid, 6), _bn(hid, 7), _bn(Cout, 8)]
+    ref = orc.patch_ir(x.float().cpu(), w.float().cpu(), hid, Cout, *bns)
+    tol = F32_TOL if dtype == torch.float32 else BF16_TOL
+    dbn = [(a.to(DEV), b.to(DEV)) for a, b in bns]
+    for lname, wl in _layouts(w).items():
+        y = ops.patch_ir(x, wl, hid, Cout, *dbn)
+        assert rel_err(y.float().cpu(), ref) < tol, lname
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("geom", [(416, 32, 5248), (224, 16, 3008), (128, 8, 704), (192, 16, 2352), (320, 4, 4216)])
+def test_heads_hyperseg_m(geom, dtype):
+    sc, groups, hp = geom
+    s = _rand((2, 1280, 16, 32), 9).abs().to(DEV, dtype)
+    out_ch = -(-hp // groups) * groups
+    ws = _rand((out_ch, sc // groups, 1, 1), 10, 0.2).to(DEV, dtype)
+    ref = orc.signal2weights(s.float().cpu(), ws.float().cpu().flatten(1), 0, sc, hp, groups)
+    tol = F32_TOL if dtype == torch.float32 else BF16_TOL
+    y = ops.signal2weights(s, ws, 0, sc, hp, groups)
+    assert y.shape == ref.shape
+    assert rel_err(y.float().cpu(), ref) < tol
+    y2 = ops.signal2weights(s.contiguous(memory_format=torch.channels_last), ws, 0, sc, hp, groups)
+    assert rel_err(y2.float().cpu(), ref) < tol
+
+
+def test_edge_shapes_fp32():
+    """Ragged / degenerate geometry: odd channels, 1x1 and 1xN patch grids, patches of 1 pixel, residual."""
+    for (B, Cin, Cout, H, W, fh, fw, g) in [(1, 3, 5, 7, 11, 7, 11, 1), (2, 9, 6, 6, 10, 3, 1, 3), (1, 1, 1, 4, 4, 1, 1, 1),
+                                            (3, 16, 8, 2, 66, 1, 33, 1)]:
+        x = _rand((B, Cin, H, W), 20).to(DEV)
+        w = _rand((B, Cout * Cin // g, fh, fw), 21, 0.3).to(DEV)
+        ref = orc.patch_conv1x1(x.cpu(), w.cpu(), Cout, g)
+        assert rel_err(ops.patch_conv1x1(x, w, Cout, g).cpu(), ref) < F32_TOL
+        assert rel_err(ops.patch_conv(x, w, Cout, (1, 1), (0, 0), groups=g).cpu(), ref) < F32_TOL
+    for (B, Cin, hid, Cout, H, W, fh, fw) in [(1, 2, 2, 2, 2, 2, 1, 1), (2, 3, 7, 3, 9, 4, 3, 2), (1, 5, 10, 33, 8, 8, 2, 2),
+                                               (1, 4, 8, 4, 48, 40, 2, 1)]:
+        hp = Cin * hid + 9 * hid + hid * Cout
+        x = _rand((B, Cin, H, W), 22).to(DEV)
+        w = _rand((B, hp, fh, fw), 23, 0.3).to(DEV)
+        bns = [_bn(hid, 24), _bn(hid, 25), _bn(Cout, 26)]
+        res = Cin == Cout
+        ref = orc.patch_ir(x.cpu(), w.cpu(), hid, Cout, *bns, residual=res)
+        y = ops.patch_ir(x, w, hid, Cout, *[(a.to(DEV), b.to(DEV)) for a, b in bns], residual=res)
+        assert rel_err(y.cpu(), ref) < F32_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# properties at BASELINE.json's full size (HyperSeg-M, batch 8, 512x1024)
+# ---------------------------------------------------------------------------------------------------------
+def _full_ir_inputs(dtype):
+    Cin, hid, Cout, H, W = M_IR["L4"]
+    hp = Cin * hid + 9 * hid + hid * Cout
+    x = _rand((8, Cin, H, W), 30).to(DEV, dtype)
+    w = ops.weights_to_patch_major(_rand((8, hp, 16, 32), 31, 0.3).to(DEV, dtype))
+    bns = [tuple(t.to(DEV) for t in _bn(n, 32 + i)) for i, n in enumerate((hid, hid, Cout))]
+    return x, w, bns, hid, Cout
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_full_size_ir_batch_independence_and_locality(dtype):
+    x, w, bns, hid, Cout = _full_ir_inputs(dtype)
+    y = ops.patch_ir(x, w, hid, Cout, *bns)
+    assert torch.isfinite(y.float()).all()
+    # an image's result does not depend on its neighbours in the batch, and equals the oracle's
+    y3 = ops.patch_ir(x[3:4].contiguous(), w[3:4], hid, Cout, *bns)
+    assert torch.equal(y3, y[3:4])
+    ref = orc.patch_ir(x[3:4].float().cpu(), w[3:4].float().cpu(), hid, Cout, *[(a.cpu(), b.cpu()) for a, b in bns])
+    assert rel_err(y3.float().cpu(), ref) < (F32_TOL if dtype == torch.float32 else BF16_TOL)
+    # changing one patch's weights changes that patch's 16x16 outputs and nothing else
+    w2 = w.clone()
+    w2[5, :, 7, 9] *= 1.5
+    y2 = ops.patch_ir(x, w2, hid, Cout, *bns)
+    diff = (y2 != y)
+    assert diff[5, :, 7 * 16:8 * 16, 9 * 16:10 * 16].any()
+    diff[5, :, 7 * 16:8 * 16, 9 * 16:10 * 16] = False
+    assert not diff.any()
+    # run-to-run determinism
+    assert torch.equal(ops.patch_ir(x, w, hid, Cout, *bns), y)
+
+
+def test_full_size_conv1x1_linearity_and_kernel_agreement():
+    Cin, Cout, H, W = M_1X1["L2"]
+    x = _rand((8, Cin, H, W), 40).to(DEV)
+    w1 = _rand((8, Cin * Cout, 16, 32), 41, 0.3).to(DEV)
+    w2 = _rand((8, Cin * Cout, 16, 32), 42, 0.3).to(DEV)
+    ya, yb, yab = (ops.patch_conv1x1(x, w, Cout) for w in (w1, w2, w1 + w2))
+    assert rel_err((ya + yb).cpu(), yab.cpu()) < 1e-5
+    # the dedicated 1x1 kernel and the generic kernel are independent implementations
+    assert rel_err(ops.patch_conv(x, w1, Cout, (1, 1), (0, 0)).cpu(), ya.cpu()) < 1e-5
+    # the fused epilogue equals a separate affine + relu
+    scale, shift = (t.to(DEV) for t in _bn(Cout, 43))
+    fused = ops.patch_conv1x1(x, w1, Cout, 1, scale, shift, "relu")
+    manual = torch.relu(ya * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    assert rel_err(fused.cpu(), manual.cpu()) < 1e-6
+
+
+def test_full_size_head_then_conv_equals_oracle_on_one_image():
+    """Head + 1x1 conv chained at level-0 size, the way the decoder runs them."""
+    sc, groups, hp, Cin, Cout = 416, 32, 5248, 82, 64
+    s = _rand((8, 1280, 16, 32), 50).abs().to(DEV)
+    ws = _rand((hp, sc // groups, 1, 1), 51, 0.2).to(DEV)
+    x = _rand((8, Cin, 16, 32), 52).to(DEV)
+    wgt = ops.signal2weights(s, ws, 0, sc, hp, groups)
+    y = ops.patch_conv1x1(x, wgt, Cout)
+    wref = orc.signal2weights(s[6:7].cpu(), ws.cpu().flatten(1), 0, sc, hp, groups)
+    yref = orc.patch_conv1x1(x[6:7].cpu(), wref, Cout)
+    assert rel_err(y[6:7].cpu(), yref) < F32_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-side behaviour on a GPU box
+# ---------------------------------------------------------------------------------------------------------
+def test_cpu_tensors_are_refused():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.patch_conv1x1(torch.zeros(1, 2, 2, 2), torch.zeros(1, 4, 1, 1), 2)
+
+
+def test_abi_errors_surface_as_exceptions():
+    from hyperseg_b200._lib import HsbError
+    x = torch.zeros(1, 4, 6, 6, device=DEV)
+    w = torch.zeros(1, 16, 4, 2, device=DEV)       # 6 % 4 != 0
+    with pytest.raises(HsbError, match="divisible"):
+        ops.patch_conv1x1(x, w, 4)
+
+
+def test_kernels_follow_the_current_stream():
+    x = _rand((2, 8, 8, 8), 60).to(DEV)
+    w = _rand((2, 32, 2, 2), 61, 0.3).to(DEV)
+    ref = ops.patch_conv1x1(x, w, 4)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        y = ops.patch_conv1x1(x, w, 4)
+    side.synchronize()
+    assert torch.equal(y, ref)
