@@ -1,11 +1,517 @@
-// bf16 tensor-core path of the fused inverted-residual MetaBlock (placeholder until the tcgen05 kernel lands).
+// Fused patch-wise inverted-residual MetaBlock -- bf16 tensor-core path (tcgen05 / TMEM / TMA), 16x16 patches.
+//
+// Same arithmetic as patch_ir.cu (reference hyperseg/models/hyperseg_v1_0.py:328-376), organised for sm_100a:
+//
+//   persistent CTAs (one per SM, 18 warps) walk the patches; for each patch
+//   P0  wait for the TMA engine: the (ph+2)x(pw+2) halo tile of x arrives through a 4-D tensor map (box
+//       24 x 18 x Cin, zero fill outside the image) and the patch's weight row through cp.async.bulk;
+//       image-border patches get their reflect halo patched in shared memory;
+//   P1  re-stage: x tile -> UMMA operand A1 (MN-major, pixels contiguous, plus a constant-one channel that
+//       carries the BatchNorm shift), W1/W3 -> operands B1/B2 with the BatchNorm scale folded in and the
+//       shift as an extra K column, W2 -> packed bf16x2 taps.  The raw buffers are then free and the TMA
+//       loads of the NEXT patch are issued, so they overlap P2..P6;
+//   P2  GEMM1 on the tensor core: H[324 px x hid] = A1 . B1^T, three M=128 tiles accumulated in TMEM;
+//   P3  epilogue 1: TMEM -> registers -> ReLU6 -> bf16 -> shared "hidden" tile [pixel][channel];
+//   P4  depthwise 3x3 + BN2 + ReLU6 on CUDA cores in packed bf16x2 (lane = channel pair, warp = tile column,
+//       3x3 register window sliding down the column), written straight into GEMM2's A operand
+//       (128B-swizzled K-major);
+//   P5  GEMM2: O[256 px x Cout] = A2 . B2^T (two M=128 tiles);
+//   P6  epilogue 2: TMEM -> registers -> bf16 -> NCHW global stores (32-byte row segments).
+//
+// The BatchNorm shifts ride inside the GEMMs (constant-one K column), so the epilogues are a clamp and a
+// convert.  Nothing but x, the weight row and y touches global memory.
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace hsb {
 
-int launch_patch_ir_tc(const void*, const void*, void*, const float* const*, int, int, int, int, int, int, int, int,
-                       int, int64_t, cudaStream_t, bool* handled) {
+constexpr int r16(int v) { return (v + 15) / 16 * 16; }
+constexpr int r8(int v) { return (v + 7) / 8 * 8; }
+
+template <int CIN_, int HID_, int COUT_>
+struct IRTC {
+    static constexpr int CIN = CIN_, HID = HID_, COUT = COUT_;
+    static constexpr int PH = 16, PW = 16, TH = 18, TW = 18, TWB = 24;
+    static constexpr int T = TH * TW, O = PH * PW;
+    static constexpr int K1 = r16(CIN + 1), N1 = r16(HID), K2 = r16(HID + 1), N2 = r16(COUT);
+    static constexpr int M1T = (T + 127) / 128, M2T = O / 128;
+    static constexpr int MC1 = M1T * 16;                   // m-chunks (8 pixels) of A1
+    static constexpr int G1 = (T + 7) / 8;                 // m-chunks that hold real pixels
+    static constexpr int HP = CIN * HID + 9 * HID + HID * COUT;
+    static constexpr int R1 = CIN * HID, R2 = R1 + 9 * HID;
+    static constexpr int NPAIR = HID / 2;
+    static constexpr int MAINP = NPAIR < 32 ? NPAIR : 32;
+    static constexpr int TAILP = NPAIR - MAINP;            // channel pairs living in the K >= 64 tail
+    static constexpr int HPITCH = r8(HID);                 // hidden tile pitch (elements), 16-byte multiple
+    static constexpr int HPW = HPITCH / 2;                 // ... in 32-bit words
+    static constexpr int KT2 = K2 > 64 ? K2 - 64 : 0;      // K extent of A2's non-swizzled tail
+    static constexpr int THREADS = 576;
+    static constexpr int D2COL = 256;                      // TMEM column of GEMM2's accumulators
+    static constexpr int TMEM_COLS = 512;
+    // UMMA operand strides (bytes)
+    static constexpr int A1_SBO = 128, A1_LBO = MC1 * 128;
+    static constexpr int B1_SBO = 128, B1_LBO = (N1 / 8) * 128;
+    static constexpr int B2_SBO = 128, B2_LBO = (N2 / 8) * 128;
+    static constexpr int A2T_SBO = 128, A2T_LBO = (O / 8) * 128;
+    // shared memory map (bytes from a 1024-aligned base)
+    static constexpr int OFF_A2 = 0;
+    static constexpr int SZ_A2 = O * 128;
+    static constexpr int OFF_A2T = OFF_A2 + SZ_A2;
+    static constexpr int SZ_A2T = (KT2 / 8) * (O / 8) * 128;
+    static constexpr int OFF_A1 = OFF_A2T + SZ_A2T;
+    static constexpr int SZ_A1 = (K1 / 8) * MC1 * 128;
+    static constexpr int OFF_B1 = OFF_A1 + SZ_A1;
+    static constexpr int SZ_B1 = (K1 / 8) * (N1 / 8) * 128;
+    static constexpr int OFF_B2 = OFF_B1 + SZ_B1;
+    static constexpr int SZ_B2 = (K2 / 8) * (N2 / 8) * 128;
+    static constexpr int OFF_HID = OFF_B2 + SZ_B2;
+    static constexpr int SZ_HID = ((T * HPITCH * 2) + 127) / 128 * 128;
+    static constexpr int ZERO_BYTES = OFF_HID + SZ_HID;    // everything above is zero-initialised once
+    static constexpr int OFF_RAWX = ZERO_BYTES;
+    static constexpr int SZ_RAWX = CIN * TH * TWB * 2;
+    static constexpr int OFF_RAWW = (OFF_RAWX + SZ_RAWX + 127) / 128 * 128;
+    static constexpr int SZ_RAWW = (HP * 2 + 15) / 16 * 16 + 16;
+    static constexpr int OFF_W2P = (OFF_RAWW + SZ_RAWW + 15) / 16 * 16;
+    static constexpr int SZ_W2P = 10 * HPW * 4;
+    static constexpr int OFF_BN = OFF_W2P + SZ_W2P;
+    static constexpr int SZ_BN = (4 * HID + 2 * COUT) * 4;
+    static constexpr int OFF_BAR = (OFF_BN + SZ_BN + 15) / 16 * 16;
+    static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;   // + slack for the 1024-byte alignment
+    static_assert(HID % 4 == 0 && HID <= 68, "hidden width must be a multiple of 4 and at most 68");
+    static_assert(TAILP <= 2, "at most two channel pairs in the K tail");
+    static_assert(M1T * N1 <= D2COL && D2COL + M2T * N2 <= TMEM_COLS, "TMEM budget");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+struct IRTCParams {
+    const __nv_bfloat16* w;
+    __nv_bfloat16* y;
+    const float* bn[6];
+    int B, H, W, fh, fw;
+    int64_t w_row_stride;      // elements between patch rows
+    int w_bulk;                // rows are 16-byte aligned -> cp.async.bulk
+    int total;                 // B * fh * fw
+};
+
+__device__ __forceinline__ uint32_t pack_relu6(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    const __nv_bfloat162 six = __floats2bfloat162_rn(6.f, 6.f);
+    __nv_bfloat162 v = __hmin2(*reinterpret_cast<__nv_bfloat162*>(&r), six);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, 1)
+patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    __nv_bfloat16* rawX = reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_RAWX);
+    __nv_bfloat16* rawW = reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_RAWW);
+    uint32_t* w2p = reinterpret_cast<uint32_t*>(sm + C::OFF_W2P);            // [10][HPW] bf16x2
+    float* bnsm = reinterpret_cast<float*>(sm + C::OFF_BN);
+    float* s1 = bnsm, *b1 = s1 + C::HID, *s2 = b1 + C::HID, *b2 = s2 + C::HID, *s3 = b2 + C::HID, *b3 = s3 + C::COUT;
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint64_t* bar_mma1 = bar_tma + 1;
+    uint64_t* bar_mma2 = bar_tma + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 3);
+
+    const uint32_t a1_addr = smem_u32(sm + C::OFF_A1), b1_addr = smem_u32(sm + C::OFF_B1);
+    const uint32_t a2_addr = smem_u32(sm + C::OFF_A2), a2t_addr = smem_u32(sm + C::OFF_A2T);
+    const uint32_t b2_addr = smem_u32(sm + C::OFF_B2);
+
+    // ---------------- one-time setup ----------------
+    for (int i = tid; i < C::ZERO_BYTES / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < C::HID; i += C::THREADS) {
+        s1[i] = p.bn[0][i]; b1[i] = p.bn[1][i]; s2[i] = p.bn[2][i]; b2[i] = p.bn[3][i];
+    }
+    for (int i = tid; i < C::COUT; i += C::THREADS) { s3[i] = p.bn[4][i]; b3[i] = p.bn[5][i]; }
+    if (tid == 0) {
+        mbar_init(bar_tma, 1);
+        mbar_init(bar_mma1, 1);
+        mbar_init(bar_mma2, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&xmap);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    __syncthreads();
+    // constant-one channels that carry the BatchNorm shifts through the GEMMs
+    {
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
+        __nv_bfloat16* a1 = reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A1);
+        for (int i = tid; i < C::MC1 * 8; i += C::THREADS) {      // A1: k = CIN, every pixel
+            int mc = i >> 3, e = i & 7;
+            a1[(size_t)(C::CIN / 8) * (C::A1_LBO / 2) + mc * (C::A1_SBO / 2) + (C::CIN % 8) * 8 + e] = one;
+        }
+        for (int m = tid; m < C::O; m += C::THREADS) {            // A2: k = HID, every pixel
+            if (C::HID < 64) {
+                int off = m * 128 + ((((C::HID / 8) ^ (m & 7)) * 16) + (C::HID % 8) * 2);
+                *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A2 + off) = one;
+            } else {
+                int k = C::HID - 64;
+                int off = (k / 8) * C::A2T_LBO + (m / 8) * C::A2T_SBO + (m & 7) * 16 + (k % 8) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A2T + off) = one;
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const int P = p.fh * p.fw;
+    constexpr uint32_t X_BYTES = C::SZ_RAWX;
+    constexpr uint32_t W_BYTES = (C::HP * 2 + 15) / 16 * 16;
+    auto issue_loads = [&](int patch) {         // one thread
+        const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
+        mbar_arrive_expect_tx(bar_tma, X_BYTES + (p.w_bulk ? W_BYTES : 0));
+        tma_load_4d(rawX, &xmap, pj * C::PW - 1, pi * C::PH - 1, 0, b, bar_tma);
+        if (p.w_bulk) bulk_g2s(rawW, p.w + (size_t)patch * p.w_row_stride, W_BYTES, bar_tma);
+    };
+    if (tid == 0 && (int)blockIdx.x < p.total) issue_loads(blockIdx.x);
+
+    constexpr uint32_t IDESC1 = idesc_bf16_f32(128, C::N1, /*A MN-major*/ true, false);
+    constexpr uint32_t IDESC2 = idesc_bf16_f32(128, C::N2, false, false);
+
+    uint32_t it = 0;
+    for (int patch = blockIdx.x; patch < p.total; patch += gridDim.x, ++it) {
+        const uint32_t par = it & 1;
+        const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
+
+        // ---------------- P0: operands of this patch have landed ----------------
+        mbar_wait(bar_tma, par);
+        if (!p.w_bulk) {
+            const __nv_bfloat16* src = p.w + (size_t)patch * p.w_row_stride;
+            for (int k = tid; k < C::HP; k += C::THREADS) rawW[k] = src[k];
+        }
+        const bool left = pj == 0, right = pj == p.fw - 1, top = pi == 0, bottom = pi == p.fh - 1;
+        if (left || right) {                       // reflect: column -1 <- column 1, column W <- column W-2
+            for (int i = tid; i < C::CIN * C::TH; i += C::THREADS) {
+                __nv_bfloat16* row = rawX + (size_t)i * C::TWB;
+                if (left) row[0] = row[2];
+                if (right) row[C::TW - 1] = row[C::TW - 3];
+            }
+            __syncthreads();
+        }
+        if (top || bottom) {
+            for (int i = tid; i < C::CIN * C::TW; i += C::THREADS) {
+                int c = i / C::TW, q = i % C::TW;
+                __nv_bfloat16* ch = rawX + (size_t)c * C::TH * C::TWB + q;
+                if (top) ch[0] = ch[2 * C::TWB];
+                if (bottom) ch[(C::TH - 1) * C::TWB] = ch[(C::TH - 3) * C::TWB];
+            }
+        }
+        if (!p.w_bulk || top || bottom) __syncthreads();
+
+        // ---------------- P1: re-stage into UMMA operand layouts ----------------
+        {   // x tile -> A1 (MN-major): unit(mc, c) = (c/8)*LBO + mc*SBO + (c%8)*16 bytes, 8 pixels per unit
+            constexpr int CB = (C::CIN + 7) / 8;
+            for (int i = tid; i < CB * C::G1 * 8; i += C::THREADS) {
+                const int c8 = i & 7, g = (i >> 3) % C::G1, cb = (i >> 3) / C::G1;
+                const int c = cb * 8 + c8;
+                if (c >= C::CIN) continue;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(rawX + (size_t)c * C::TH * C::TWB);
+                uint32_t v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int px = g * 8 + e * 2;                 // even -> (px, px+1) sit in one tile row
+                    const int r = px / C::TW, q = px % C::TW;
+                    v[e] = px < C::T ? src[(r * C::TWB + q) >> 1] : 0u;
+                }
+                *reinterpret_cast<uint4*>(sm + C::OFF_A1 + cb * C::A1_LBO + g * C::A1_SBO + c8 * 16) =
+                    make_uint4(v[0], v[1], v[2], v[3]);
+            }
+            // W1 -> B1 (K-major): unit(n, kc) = kc*LBO + (n/8)*SBO + (n%8)*16; row n = s1[n]*W1[n][:], b1[n] at k=CIN
+            constexpr int KC1 = (C::CIN + 1 + 7) / 8;
+            for (int i = tid; i < C::HID * KC1; i += C::THREADS) {
+                const int n = i / KC1, kc = i % KC1;
+                const float sc = s1[n];
+                const __nv_bfloat16* src = rawW + n * C::CIN;
+                uint32_t v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float f[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = kc * 8 + e * 2 + h;
+                        f[h] = k < C::CIN ? __bfloat162float(src[k]) * sc : (k == C::CIN ? b1[n] : 0.f);
+                    }
+                    __nv_bfloat162 t = __floats2bfloat162_rn(f[0], f[1]);
+                    v[e] = *reinterpret_cast<uint32_t*>(&t);
+                }
+                *reinterpret_cast<uint4*>(sm + C::OFF_B1 + kc * C::B1_LBO + (n >> 3) * C::B1_SBO + (n & 7) * 16) =
+                    make_uint4(v[0], v[1], v[2], v[3]);
+            }
+            // W3 -> B2 (K-major): row n = s3[n]*W3[n][:], b3[n] at k=HID
+            constexpr int KC2 = (C::HID + 1 + 7) / 8;
+            for (int i = tid; i < C::COUT * KC2; i += C::THREADS) {
+                const int n = i / KC2, kc = i % KC2;
+                const float sc = s3[n];
+                const __nv_bfloat16* src = rawW + C::R2 + n * C::HID;
+                uint32_t v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float f[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = kc * 8 + e * 2 + h;
+                        f[h] = k < C::HID ? __bfloat162float(src[k]) * sc : (k == C::HID ? b3[n] : 0.f);
+                    }
+                    __nv_bfloat162 t = __floats2bfloat162_rn(f[0], f[1]);
+                    v[e] = *reinterpret_cast<uint32_t*>(&t);
+                }
+                *reinterpret_cast<uint4*>(sm + C::OFF_B2 + kc * C::B2_LBO + (n >> 3) * C::B2_SBO + (n & 7) * 16) =
+                    make_uint4(v[0], v[1], v[2], v[3]);
+            }
+            // W2 -> packed taps: w2p[tap][cp] = (s2*W2[2cp][tap], s2*W2[2cp+1][tap]); w2p[9][cp] = (b2, b2)
+            for (int i = tid; i < 10 * C::NPAIR; i += C::THREADS) {
+                const int tap = i / C::NPAIR, cp = i % C::NPAIR;
+                float lo, hi;
+                if (tap < 9) {
+                    lo = __bfloat162float(rawW[C::R1 + (2 * cp) * 9 + tap]) * s2[2 * cp];
+                    hi = __bfloat162float(rawW[C::R1 + (2 * cp + 1) * 9 + tap]) * s2[2 * cp + 1];
+                } else {
+                    lo = b2[2 * cp]; hi = b2[2 * cp + 1];
+                }
+                __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+                w2p[tap * C::HPW + cp] = *reinterpret_cast<uint32_t*>(&t);
+            }
+        }
+        fence_proxy_async_smem();          // operand writes -> visible to the tensor core (async proxy)
+        tc_fence_before_sync();
+        __syncthreads();
+
+        // ---------------- P2: GEMM1 + prefetch of the next patch ----------------
+        if (tid == 0) {
+            tc_fence_after_sync();
+            for (int t = 0; t < C::M1T; ++t) {
+#pragma unroll
+                for (int s = 0; s < C::K1 / 16; ++s) {
+                    const uint64_t da = smem_desc(a1_addr + 2 * s * C::A1_LBO + t * 16 * C::A1_SBO, C::A1_LBO, C::A1_SBO, SWZ_NONE);
+                    const uint64_t db = smem_desc(b1_addr + 2 * s * C::B1_LBO, C::B1_LBO, C::B1_SBO, SWZ_NONE);
+                    umma_bf16(tmem + t * C::N1, da, db, IDESC1, s > 0);
+                }
+            }
+            umma_commit(bar_mma1);
+            const int next = patch + gridDim.x;
+            if (next < p.total) issue_loads(next);     // raw buffers were fully consumed in P1
+        }
+
+        // ---------------- P3: epilogue 1 (TMEM -> ReLU6 -> hidden tile) ----------------
+        mbar_wait(bar_mma1, par);
+        tc_fence_after_sync();
+        if (warp < 4 * C::M1T) {
+            const int t = warp >> 2, q = warp & 3;
+            const int m = t * 128 + q * 32 + lane;
+            if (t * 128 + q * 32 < C::T) {                     // warp-uniform: this quadrant holds real pixels
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + t * C::N1;
+                unsigned char* hrow = sm + C::OFF_HID + (size_t)m * (C::HPITCH * 2);
+                constexpr int FULL = C::HID / 16, REM = C::HID % 16;
+#pragma unroll
+                for (int ch = 0; ch < FULL; ++ch) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + ch * 16, v);
+                    tmem_ld_wait();
+                    uint32_t o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = pack_relu6(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    if (m < C::T) {
+                        *reinterpret_cast<uint4*>(hrow + ch * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4*>(hrow + ch * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+                if (REM >= 8) {
+                    uint32_t v[8];
+                    tmem_ld8(taddr + FULL * 16, v);
+                    tmem_ld_wait();
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = pack_relu6(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    if (m < C::T) *reinterpret_cast<uint4*>(hrow + FULL * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                if (REM % 8 == 4) {
+                    constexpr int c0 = FULL * 16 + (REM >= 8 ? 8 : 0);
+                    uint32_t v[4];
+                    tmem_ld4(taddr + c0, v);
+                    tmem_ld_wait();
+                    uint32_t o0 = pack_relu6(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                    uint32_t o1 = pack_relu6(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                    if (m < C::T) *reinterpret_cast<uint2*>(hrow + c0 * 2) = make_uint2(o0, o1);
+                }
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+
+        // ---------------- P4: depthwise 3x3 + BN2 + ReLU6 -> A2 ----------------
+        {
+            const uint32_t* hid = reinterpret_cast<const uint32_t*>(sm + C::OFF_HID);
+            int cp = -1, v = 0;
+            bool tail = false;
+            if (warp < C::PW) { if (lane < C::MAINP) { cp = lane; v = warp; } }
+            else if (warp == C::PW && C::TAILP > 0) {
+                if ((lane % 2) < C::TAILP) { cp = 32 + (lane & 1); v = lane >> 1; tail = true; }
+            }
+            if (cp >= 0) {
+                __nv_bfloat162 wt[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) wt[k] = *reinterpret_cast<const __nv_bfloat162*>(&w2p[k * C::HPW + cp]);
+                const __nv_bfloat162 bias = *reinterpret_cast<const __nv_bfloat162*>(&w2p[9 * C::HPW + cp]);
+                const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f), six = __floats2bfloat162_rn(6.f, 6.f);
+                const uint32_t* col = hid + v * C::HPW + cp;               // pixel (r, v + kx) at (r*TW + v + kx)*HPW
+                __nv_bfloat162 r0[3], r1[3], r2[3];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    uint32_t a = col[(0 * C::TW + kx) * C::HPW], bq = col[(1 * C::TW + kx) * C::HPW];
+                    r0[kx] = *reinterpret_cast<__nv_bfloat162*>(&a);
+                    r1[kx] = *reinterpret_cast<__nv_bfloat162*>(&bq);
+                }
+#pragma unroll
+                for (int u = 0; u < C::PH; ++u) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        uint32_t a = col[((u + 2) * C::TW + kx) * C::HPW];
+                        r2[kx] = *reinterpret_cast<__nv_bfloat162*>(&a);
+                    }
+                    __nv_bfloat162 acc = bias;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        acc = __hfma2(wt[kx], r0[kx], acc);
+                        acc = __hfma2(wt[3 + kx], r1[kx], acc);
+                        acc = __hfma2(wt[6 + kx], r2[kx], acc);
+                    }
+                    acc = __hmin2(__hmax2(acc, zero), six);
+                    const int m = u * C::PW + v;
+                    uint32_t off;
+                    if (!tail) off = C::OFF_A2 + m * 128 + ((((cp >> 2) ^ (m & 7)) << 4) | ((cp & 3) << 2));
+                    else off = C::OFF_A2T + (m >> 3) * C::A2T_SBO + (m & 7) * 16 + (cp - 32) * 4;
+                    *reinterpret_cast<uint32_t*>(sm + off) = *reinterpret_cast<uint32_t*>(&acc);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) { r0[kx] = r1[kx]; r1[kx] = r2[kx]; }
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+
+        // ---------------- P5: GEMM2 ----------------
+        if (tid == 0) {
+            tc_fence_after_sync();
+            for (int t = 0; t < C::M2T; ++t) {
+#pragma unroll
+                for (int s = 0; s < C::K2 / 16; ++s) {
+                    uint64_t da;
+                    if (s < 4) da = smem_desc(a2_addr + t * 128 * 128 + s * 32, 16, 1024, SWZ_128B);
+                    else da = smem_desc(a2t_addr + 2 * (s - 4) * C::A2T_LBO + t * 16 * C::A2T_SBO, C::A2T_LBO, C::A2T_SBO, SWZ_NONE);
+                    const uint64_t db = smem_desc(b2_addr + 2 * s * C::B2_LBO, C::B2_LBO, C::B2_SBO, SWZ_NONE);
+                    umma_bf16(tmem + C::D2COL + t * C::N2, da, db, IDESC2, s > 0);
+                }
+            }
+            umma_commit(bar_mma2);
+        }
+
+        // ---------------- P6: epilogue 2 (TMEM -> bf16 -> NCHW) ----------------
+        mbar_wait(bar_mma2, par);
+        tc_fence_after_sync();
+        if (warp < 4 * C::M2T) {
+            const int t = warp >> 2, q = warp & 3;
+            const int m = t * 128 + q * 32 + lane;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + C::D2COL + t * C::N2;
+            const int u = m / C::PW, vv = m % C::PW;
+            __nv_bfloat16* yp = p.y + (((size_t)b * C::COUT) * p.H + (size_t)pi * C::PH + u) * p.W + (size_t)pj * C::PW + vv;
+            const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+            for (int c0 = 0; c0 < C::COUT; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + c0, v);          // N2 is a multiple of 16, so this never leaves the accumulator
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    if (c0 + e < C::COUT) yp[(size_t)(c0 + e) * plane] = __float2bfloat16_rn(__uint_as_float(v[e]));
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();       // TMEM and the operand buffers are reused by the next patch
+        tc_fence_after_sync();
+    }
+
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static std::once_flag once;
+    static EncodeTiledFn fn = nullptr;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+template <class C>
+static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return fail(HSB_ERR_CUDA, "patch_ir_tc: cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)C::CIN, (cuuint64_t)p.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.W * 2, (cuuint64_t)p.W * p.H * 2, (cuuint64_t)p.W * p.H * C::CIN * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)C::TWB, (cuuint32_t)C::TH, (cuuint32_t)C::CIN, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HSB_ERR_CUDA, "patch_ir_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    auto kern = patch_ir_tc_kernel<C>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("patch_ir_tc attr: ") + cudaGetErrorString(e));
+    const int grid = std::min(p.total, std::max(1, device_sm_count()));
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
+    return check_launch("patch_ir_tc launch");
+}
+
+int launch_patch_ir_tc(const void* x, const void* w, void* y, const float* const* bn, int B, int Cin, int hid, int Cout,
+                       int H, int W, int fh, int fw, int residual, int64_t w_row_stride, cudaStream_t st, bool* handled) {
     *handled = false;
+    static const bool disabled = [] { const char* e = getenv("HSB_DISABLE_TC"); return e && e[0] == '1'; }();
+    if (disabled || residual) return HSB_OK;
+    if (H / fh != 16 || W / fw != 16) return HSB_OK;
+    if ((W % 8) != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return HSB_OK;      // TMA: 16-byte strides / base
+    IRTCParams p;
+    p.w = reinterpret_cast<const __nv_bfloat16*>(w);
+    p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    for (int i = 0; i < 6; ++i) p.bn[i] = bn[i];
+    p.B = B; p.H = H; p.W = W; p.fh = fh; p.fw = fw; p.w_row_stride = w_row_stride; p.total = B * fh * fw;
+    const int64_t hp = (int64_t)Cin * hid + 9 * hid + (int64_t)hid * Cout;
+    // bulk copies move ceil16(hp*2) bytes per row: the row (incl. that round-up) must stay inside its stride
+    p.w_bulk = ((reinterpret_cast<uintptr_t>(w) & 15) == 0) && ((w_row_stride * 2) % 16 == 0) &&
+               (((hp * 2 + 15) / 16 * 16) <= w_row_stride * 2);
+#define HSB_TC_CASE(CI, HD, CO)                                   \
+    if (Cin == CI && hid == HD && Cout == CO) {                   \
+        *handled = true;                                          \
+        return launch_tc<IRTC<CI, HD, CO>>(x, p, st);             \
+    }
+    HSB_TC_CASE(34, 68, 19)      // HyperSeg-M level 4
+    HSB_TC_CASE(26, 52, 19)      // HyperSeg-S Cityscapes level 4
+    HSB_TC_CASE(22, 44, 12)      // HyperSeg-S CamVid level 4
+#undef HSB_TC_CASE
     return HSB_OK;
 }
 
