@@ -4,7 +4,7 @@
 //
 //   persistent CTAs (one per SM, 18 warps) walk the patches; for each patch
 //   P0  wait for the TMA engine: the (ph+2)x(pw+2) halo tile of x arrives through a 4-D tensor map (box
-//       24 x 18 x Cin, zero fill outside the image) and the patch's weight row through cp.async.bulk;
+//       32 x 18 x Cin starting 8 pixels left of the patch -- TMA wants 16-byte aligned rows --, zero fill outside the image) and the patch's weight row through cp.async.bulk;
 //       image-border patches get their reflect halo patched in shared memory;
 //   P1  re-stage: x tile -> UMMA operand A1 (MN-major, pixels contiguous, plus a constant-one channel that
 //       carries the BatchNorm shift), W1/W3 -> operands B1/B2 with the BatchNorm scale folded in and the
@@ -35,7 +35,10 @@ constexpr int r8(int v) { return (v + 7) / 8 * 8; }
 template <int CIN_, int HID_, int COUT_>
 struct IRTC {
     static constexpr int CIN = CIN_, HID = HID_, COUT = COUT_;
-    static constexpr int PH = 16, PW = 16, TH = 18, TW = 18, TWB = 24;
+    static constexpr int PH = 16, PW = 16, TH = 18, TW = 18;
+    // TMA needs a 16-byte aligned start in the innermost dimension: the box starts 8 pixels left of the patch
+    // (32 pixels wide), the halo tile's column 0 is box column XOFF.
+    static constexpr int TWB = 32, XOFF = 7;
     static constexpr int T = TH * TW, O = PH * PW;
     static constexpr int K1 = r16(CIN + 1), N1 = r16(HID), K2 = r16(HID + 1), N2 = r16(COUT);
     static constexpr int M1T = (T + 127) / 128, M2T = O / 128;
@@ -171,7 +174,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     auto issue_loads = [&](int patch) {         // one thread
         const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
         mbar_arrive_expect_tx(bar_tma, X_BYTES + (p.w_bulk ? W_BYTES : 0));
-        tma_load_4d(rawX, &xmap, pj * C::PW - 1, pi * C::PH - 1, 0, b, bar_tma);
+        tma_load_4d(rawX, &xmap, pj * C::PW - 8, pi * C::PH - 1, 0, b, bar_tma);
         if (p.w_bulk) bulk_g2s(rawW, p.w + (size_t)patch * p.w_row_stride, W_BYTES, bar_tma);
     };
     if (tid == 0 && (int)blockIdx.x < p.total) issue_loads(blockIdx.x);
@@ -193,7 +196,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         const bool left = pj == 0, right = pj == p.fw - 1, top = pi == 0, bottom = pi == p.fh - 1;
         if (left || right) {                       // reflect: column -1 <- column 1, column W <- column W-2
             for (int i = tid; i < C::CIN * C::TH; i += C::THREADS) {
-                __nv_bfloat16* row = rawX + (size_t)i * C::TWB;
+                __nv_bfloat16* row = rawX + (size_t)i * C::TWB + C::XOFF;
                 if (left) row[0] = row[2];
                 if (right) row[C::TW - 1] = row[C::TW - 3];
             }
@@ -202,7 +205,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         if (top || bottom) {
             for (int i = tid; i < C::CIN * C::TW; i += C::THREADS) {
                 int c = i / C::TW, q = i % C::TW;
-                __nv_bfloat16* ch = rawX + (size_t)c * C::TH * C::TWB + q;
+                __nv_bfloat16* ch = rawX + (size_t)c * C::TH * C::TWB + C::XOFF + q;
                 if (top) ch[0] = ch[2 * C::TWB];
                 if (bottom) ch[(C::TH - 1) * C::TWB] = ch[(C::TH - 3) * C::TWB];
             }
@@ -216,13 +219,18 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                 const int c8 = i & 7, g = (i >> 3) % C::G1, cb = (i >> 3) / C::G1;
                 const int c = cb * 8 + c8;
                 if (c >= C::CIN) continue;
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(rawX + (size_t)c * C::TH * C::TWB);
+                const __nv_bfloat16* src = rawX + (size_t)c * C::TH * C::TWB + C::XOFF;
                 uint32_t v[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int px = g * 8 + e * 2;                 // even -> (px, px+1) sit in one tile row
                     const int r = px / C::TW, q = px % C::TW;
-                    v[e] = px < C::T ? src[(r * C::TWB + q) >> 1] : 0u;
+                    uint32_t lo = 0, hi = 0;
+                    if (px < C::T) {
+                        lo = *reinterpret_cast<const unsigned short*>(src + r * C::TWB + q);
+                        hi = *reinterpret_cast<const unsigned short*>(src + r * C::TWB + q + 1);
+                    }
+                    v[e] = lo | (hi << 16);
                 }
                 *reinterpret_cast<uint4*>(sm + C::OFF_A1 + cb * C::A1_LBO + g * C::A1_SBO + c8 * 16) =
                     make_uint4(v[0], v[1], v[2], v[3]);
