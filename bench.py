@@ -116,7 +116,9 @@ def cpu_forward_fps(steps: int, warmup: int, budget_s: float | None):
     from hyperseg_b200.synthetic import build_model, synthetic_frames
     from oracle import hyperseg_oracle as orc
 
-    cores = os.cpu_count() or 1
+    # more than ~16 threads makes torch's CPU kernels slower on the many-core bench hosts (measured: 8 thr 29 ms,
+    # 16 thr 25 ms, 32 thr 47 ms, 128 thr 9.5 s per 128x256 frame), so the baseline uses its best setting
+    cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     model = build_model(CONFIG, seed=0)
     frames = [synthetic_frames(1, HEIGHT, WIDTH, seed=2 + i) for i in range(2)]
@@ -360,7 +362,7 @@ def run_ours(args):
             line["cpu_baseline"] = {
                 "value": r["fps"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                 "sample": f"{r['frames']} single-frame 1024x512 forwards in {r['seconds']:.1f} s (fp32, stock torch "
-                          f"encoder + oracle decoder, {r['cores']} threads)"}
+                          f"encoder + oracle decoder, {r['cores']} threads of {os.cpu_count()} cores)"}
         else:
             line["cpu_baseline"] = None
     if world > 1:

@@ -121,9 +121,9 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     float* bnsm = reinterpret_cast<float*>(sm + C::OFF_BN);
     float* s1 = bnsm, *b1 = s1 + C::HID, *s2 = b1 + C::HID, *b2 = s2 + C::HID, *s3 = b2 + C::HID, *b3 = s3 + C::COUT;
     uint64_t* bar_tma = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
-    uint64_t* bar_mma1 = bar_tma + 1;
-    uint64_t* bar_mma2 = bar_tma + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 3);
+    uint64_t* bar_mma1 = bar_tma + 1;                     // [M1T] one per GEMM1 tile
+    uint64_t* bar_mma2 = bar_mma1 + C::M1T;               // [M2T]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma2 + C::M2T);
 
     const uint32_t a1_addr = smem_u32(sm + C::OFF_A1), b1_addr = smem_u32(sm + C::OFF_B1);
     const uint32_t a2_addr = smem_u32(sm + C::OFF_A2), a2t_addr = smem_u32(sm + C::OFF_A2T);
@@ -137,8 +137,8 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     for (int i = tid; i < C::COUT; i += C::THREADS) { s3[i] = p.bn[4][i]; b3[i] = p.bn[5][i]; }
     if (tid == 0) {
         mbar_init(bar_tma, 1);
-        mbar_init(bar_mma1, 1);
-        mbar_init(bar_mma2, 1);
+        for (int t = 0; t < C::M1T; ++t) mbar_init(bar_mma1 + t, 1);
+        for (int t = 0; t < C::M2T; ++t) mbar_init(bar_mma2 + t, 1);
         mbar_fence_init();
         tma_prefetch_desc(&xmap);
     }
@@ -147,11 +147,6 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     // constant-one channels that carry the BatchNorm shifts through the GEMMs
     {
         const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
-        __nv_bfloat16* a1 = reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A1);
-        for (int i = tid; i < C::MC1 * 8; i += C::THREADS) {      // A1: k = CIN, every pixel
-            int mc = i >> 3, e = i & 7;
-            a1[(size_t)(C::CIN / 8) * (C::A1_LBO / 2) + mc * (C::A1_SBO / 2) + (C::CIN % 8) * 8 + e] = one;
-        }
         for (int m = tid; m < C::O; m += C::THREADS) {            // A2: k = HID, every pixel
             if (C::HID < 64) {
                 int off = m * 128 + ((((C::HID / 8) ^ (m & 7)) * 16) + (C::HID % 8) * 2);
@@ -179,7 +174,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     };
     if (tid == 0 && (int)blockIdx.x < p.total) issue_loads(blockIdx.x);
 
-    constexpr uint32_t IDESC1 = idesc_bf16_f32(128, C::N1, /*A MN-major*/ true, false);
+    constexpr uint32_t IDESC1 = idesc_bf16_f32(128, C::N1, false, false);
     constexpr uint32_t IDESC2 = idesc_bf16_f32(128, C::N2, false, false);
 
     uint32_t it = 0;
@@ -213,27 +208,28 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         if (!p.w_bulk || top || bottom) __syncthreads();
 
         // ---------------- P1: re-stage into UMMA operand layouts ----------------
-        {   // x tile -> A1 (MN-major): unit(mc, c) = (c/8)*LBO + mc*SBO + (c%8)*16 bytes, 8 pixels per unit
-            constexpr int CB = (C::CIN + 7) / 8;
-            for (int i = tid; i < CB * C::G1 * 8; i += C::THREADS) {
-                const int c8 = i & 7, g = (i >> 3) % C::G1, cb = (i >> 3) / C::G1;
-                const int c = cb * 8 + c8;
-                if (c >= C::CIN) continue;
-                const __nv_bfloat16* src = rawX + (size_t)c * C::TH * C::TWB + C::XOFF;
-                uint32_t v[4];
+        {   // x tile -> A1 (K-major): unit(m, kc) = kc*LBO + (m/8)*SBO + (m%8)*16 bytes = 8 channels of pixel m.
+            // Lanes walk consecutive pixels: 2-byte reads of one tile row are contiguous, the 16-byte writes of a
+            // warp cover 512 contiguous bytes -> no bank conflicts either way.  Channel CIN is the constant one.
+            constexpr int KCX = (C::CIN + 1 + 7) / 8;
+            constexpr int CHS = C::TH * C::TWB;                    // elements between channels of the raw tile
+            for (int i = tid; i < KCX * C::T; i += C::THREADS) {
+                const int m = i % C::T, kc = i / C::T;
+                const unsigned short* src = reinterpret_cast<const unsigned short*>(rawX) + (m / C::TW) * C::TWB +
+                                            (m % C::TW) + C::XOFF + kc * 8 * CHS;
+                uint32_t h[8];
+                if (kc < C::CIN / 8) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int px = g * 8 + e * 2;                 // even -> (px, px+1) sit in one tile row
-                    const int r = px / C::TW, q = px % C::TW;
-                    uint32_t lo = 0, hi = 0;
-                    if (px < C::T) {
-                        lo = *reinterpret_cast<const unsigned short*>(src + r * C::TWB + q);
-                        hi = *reinterpret_cast<const unsigned short*>(src + r * C::TWB + q + 1);
+                    for (int e = 0; e < 8; ++e) h[e] = src[e * CHS];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        constexpr int k0 = (C::CIN / 8) * 8;
+                        h[e] = (k0 + e < C::CIN) ? (uint32_t)src[e * CHS] : ((k0 + e == C::CIN) ? 0x3F80u : 0u);
                     }
-                    v[e] = lo | (hi << 16);
                 }
-                *reinterpret_cast<uint4*>(sm + C::OFF_A1 + cb * C::A1_LBO + g * C::A1_SBO + c8 * 16) =
-                    make_uint4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<uint4*>(sm + C::OFF_A1 + kc * C::A1_LBO + (m >> 3) * C::A1_SBO + (m & 7) * 16) =
+                    make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
             }
             // W1 -> B1 (K-major): unit(n, kc) = kc*LBO + (n/8)*SBO + (n%8)*16; row n = s1[n]*W1[n][:], b1[n] at k=CIN
             constexpr int KC1 = (C::CIN + 1 + 7) / 8;
@@ -305,52 +301,63 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                     const uint64_t db = smem_desc(b1_addr + 2 * s * C::B1_LBO, C::B1_LBO, C::B1_SBO, SWZ_NONE);
                     umma_bf16(tmem + t * C::N1, da, db, IDESC1, s > 0);
                 }
+                umma_commit(bar_mma1 + t);          // epilogue of tile t can start while the next tile runs
             }
-            umma_commit(bar_mma1);
             const int next = patch + gridDim.x;
             if (next < p.total) issue_loads(next);     // raw buffers were fully consumed in P1
         }
 
         // ---------------- P3: epilogue 1 (TMEM -> ReLU6 -> hidden tile) ----------------
-        mbar_wait(bar_mma1, par);
-        tc_fence_after_sync();
         if (warp < 4 * C::M1T) {
             const int t = warp >> 2, q = warp & 3;
             const int m = t * 128 + q * 32 + lane;
             if (t * 128 + q * 32 < C::T) {                     // warp-uniform: this quadrant holds real pixels
+                mbar_wait(bar_mma1 + t, par);
+                tc_fence_after_sync();
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + t * C::N1;
                 unsigned char* hrow = sm + C::OFF_HID + (size_t)m * (C::HPITCH * 2);
                 constexpr int FULL = C::HID / 16, REM = C::HID % 16;
+                static_assert(REM == 0 || REM == 4 || REM == 8 || REM == 12, "hidden width must be a multiple of 4");
+                // 32 columns per round trip: two loads in flight, one wait
 #pragma unroll
-                for (int ch = 0; ch < FULL; ++ch) {
-                    uint32_t v[16];
-                    tmem_ld16(taddr + ch * 16, v);
+                for (int ch = 0; ch < FULL; ch += 2) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(taddr + ch * 16, v0);
+                    if (ch + 1 < FULL) tmem_ld16(taddr + (ch + 1) * 16, v1);
                     tmem_ld_wait();
                     uint32_t o[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = pack_relu6(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                    for (int e = 0; e < 8; ++e) o[e] = pack_relu6(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1]));
                     if (m < C::T) {
                         *reinterpret_cast<uint4*>(hrow + ch * 32) = make_uint4(o[0], o[1], o[2], o[3]);
                         *reinterpret_cast<uint4*>(hrow + ch * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
                     }
-                }
-                if (REM >= 8) {
-                    uint32_t v[8];
-                    tmem_ld8(taddr + FULL * 16, v);
-                    tmem_ld_wait();
-                    uint32_t o[4];
+                    if (ch + 1 < FULL) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = pack_relu6(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-                    if (m < C::T) *reinterpret_cast<uint4*>(hrow + FULL * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                        for (int e = 0; e < 8; ++e) o[e] = pack_relu6(__uint_as_float(v1[2 * e]), __uint_as_float(v1[2 * e + 1]));
+                        if (m < C::T) {
+                            *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
                 }
-                if (REM % 8 == 4) {
-                    constexpr int c0 = FULL * 16 + (REM >= 8 ? 8 : 0);
-                    uint32_t v[4];
-                    tmem_ld4(taddr + c0, v);
+                if (REM > 0) {
+                    uint32_t v8[8], v4[4];
+                    if (REM >= 8) tmem_ld8(taddr + FULL * 16, v8);
+                    constexpr int c4 = FULL * 16 + (REM >= 8 ? 8 : 0);
+                    if (REM % 8 == 4) tmem_ld4(taddr + c4, v4);
                     tmem_ld_wait();
-                    uint32_t o0 = pack_relu6(__uint_as_float(v[0]), __uint_as_float(v[1]));
-                    uint32_t o1 = pack_relu6(__uint_as_float(v[2]), __uint_as_float(v[3]));
-                    if (m < C::T) *reinterpret_cast<uint2*>(hrow + c0 * 2) = make_uint2(o0, o1);
+                    if (REM >= 8) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = pack_relu6(__uint_as_float(v8[2 * e]), __uint_as_float(v8[2 * e + 1]));
+                        if (m < C::T) *reinterpret_cast<uint4*>(hrow + FULL * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                    if (REM % 8 == 4) {
+                        uint32_t o0 = pack_relu6(__uint_as_float(v4[0]), __uint_as_float(v4[1]));
+                        uint32_t o1 = pack_relu6(__uint_as_float(v4[2]), __uint_as_float(v4[3]));
+                        if (m < C::T) *reinterpret_cast<uint2*>(hrow + c4 * 2) = make_uint2(o0, o1);
+                    }
                 }
             }
         }
@@ -421,15 +428,15 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                     const uint64_t db = smem_desc(b2_addr + 2 * s * C::B2_LBO, C::B2_LBO, C::B2_SBO, SWZ_NONE);
                     umma_bf16(tmem + C::D2COL + t * C::N2, da, db, IDESC2, s > 0);
                 }
+                umma_commit(bar_mma2 + t);
             }
-            umma_commit(bar_mma2);
         }
 
         // ---------------- P6: epilogue 2 (TMEM -> bf16 -> NCHW) ----------------
-        mbar_wait(bar_mma2, par);
-        tc_fence_after_sync();
         if (warp < 4 * C::M2T) {
             const int t = warp >> 2, q = warp & 3;
+            mbar_wait(bar_mma2 + t, par);
+            tc_fence_after_sync();
             const int m = t * 128 + q * 32 + lane;
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + C::D2COL + t * C::N2;
             const int u = m / C::PW, vv = m % C::PW;

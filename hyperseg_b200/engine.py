@@ -68,7 +68,8 @@ def fold_static_batchnorms(model: nn.Module) -> int:
 
 class SegmentationEngine:
     def __init__(self, model: nn.Module, batch: int, height: int, width: int, device="cuda",
-                 dtype=torch.bfloat16, use_graph: bool = True, fold_bn: bool = True, warmup: int = 3):
+                 dtype=torch.bfloat16, use_graph: bool = True, fold_bn: bool = True, warmup: int = 3,
+                 channels_last: bool = True):
         self.device = torch.device(device)
         self.dtype = dtype
         self.shape = (batch, 3, height, width)
@@ -82,6 +83,12 @@ class SegmentationEngine:
             if isinstance(m, nn.BatchNorm2d) and m.running_mean is not None:
                 pinned.append((m, ops.fold_bn(m)))
         self.net = net.to(self.device, dtype)
+        self.channels_last = channels_last
+        if channels_last:
+            # cuDNN's bf16 kernels want NHWC; the decoder kernels want NCHW, so the (small) feature maps the
+            # encoder hands over are converted back where the decoder concatenates them
+            self.net.backbone.to(memory_format=torch.channels_last)
+            self.net.weight_mapper.to(memory_format=torch.channels_last)
         for m, (scale, shift) in pinned:
             m._hsb_folded = (scale.to(self.device, torch.float32).contiguous(),
                              shift.to(self.device, torch.float32).contiguous())
@@ -109,7 +116,13 @@ class SegmentationEngine:
 
     def _forward_static(self):
         x = self.frames_dev.to(self.dtype)
-        self.logits = self.net(x)
+        if self.channels_last:
+            net = self.net
+            feats = net.backbone(x.contiguous(memory_format=torch.channels_last))
+            signal = net.weight_mapper(feats[-1])
+            self.logits = net.decoder([x] + [f.contiguous() for f in feats[:-1]], signal)
+        else:
+            self.logits = self.net(x)
         self.labels = self.logits.argmax(1).to(torch.uint8)
 
     @torch.no_grad()

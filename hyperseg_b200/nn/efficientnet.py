@@ -72,10 +72,14 @@ class SamePadConv2d(nn.Conv2d):
         need_w = max((math.ceil(iw / sw) - 1) * sw + (kw - 1) * self.dilation[1] + 1 - iw, 0)
         # (left, right, top, bottom): the odd pixel goes to the right / bottom
         self.same_pad = (need_w // 2, need_w - need_w // 2, need_h // 2, need_h - need_h // 2)
+        # a symmetric pad is handed to the convolution itself (no padded copy of the activation)
+        self.symmetric = need_w % 2 == 0 and need_h % 2 == 0
+        self.conv_pad = (need_h // 2, need_w // 2)
 
     def forward(self, x):
-        if any(self.same_pad):
-            x = F.pad(x, self.same_pad)
+        if self.symmetric:
+            return F.conv2d(x, self.weight, self.bias, self.stride, self.conv_pad, self.dilation, self.groups)
+        x = F.pad(x, self.same_pad)
         return F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
 
 
