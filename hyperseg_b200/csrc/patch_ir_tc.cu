@@ -32,16 +32,20 @@ namespace hsb {
 constexpr int r16(int v) { return (v + 15) / 16 * 16; }
 constexpr int r8(int v) { return (v + 7) / 8 * 8; }
 
-template <int CIN_, int HID_, int COUT_>
+constexpr int pow2_at_least(int v) { int p = 32; while (p < v) p *= 2; return p; }
+constexpr int imax(int a, int b) { return a > b ? a : b; }
+
+template <int CIN_, int HID_, int COUT_, int PS_>
 struct IRTC {
     static constexpr int CIN = CIN_, HID = HID_, COUT = COUT_;
-    static constexpr int PH = 16, PW = 16, TH = 18, TW = 18;
+    static constexpr int PH = PS_, PW = PS_, TH = PS_ + 2, TW = PS_ + 2;
     // TMA needs a 16-byte aligned start in the innermost dimension: the box starts 8 pixels left of the patch
     // (32 pixels wide), the halo tile's column 0 is box column XOFF.
-    static constexpr int TWB = 32, XOFF = 7;
+    static constexpr int XOFF = 7, TWB = r8(XOFF + TW);
     static constexpr int T = TH * TW, O = PH * PW;
     static constexpr int K1 = r16(CIN + 1), N1 = r16(HID), K2 = r16(HID + 1), N2 = r16(COUT);
-    static constexpr int M1T = (T + 127) / 128, M2T = O / 128;
+    static constexpr int M1T = (T + 127) / 128, M2T = (O + 127) / 128;
+    static constexpr int MC2 = M2T * 16;                   // m-chunks of A2
     static constexpr int MC1 = M1T * 16;                   // m-chunks (8 pixels) of A1
     static constexpr int G1 = (T + 7) / 8;                 // m-chunks that hold real pixels
     static constexpr int HP = CIN * HID + 9 * HID + HID * COUT;
@@ -52,19 +56,21 @@ struct IRTC {
     static constexpr int HPITCH = r8(HID);                 // hidden tile pitch (elements), 16-byte multiple
     static constexpr int HPW = HPITCH / 2;                 // ... in 32-bit words
     static constexpr int KT2 = K2 > 64 ? K2 - 64 : 0;      // K extent of A2's non-swizzled tail
-    static constexpr int THREADS = 576;
-    static constexpr int D2COL = 256;                      // TMEM column of GEMM2's accumulators
-    static constexpr int TMEM_COLS = 512;
+    static constexpr int DW_WARPS = PW + (TAILP > 0 ? 1 : 0);
+    static constexpr int WARPS = imax(imax(4 * M1T, 4 * M2T), DW_WARPS);
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int D2COL = r16(M1T * N1);            // TMEM column of GEMM2's accumulators
+    static constexpr int TMEM_COLS = pow2_at_least(D2COL + M2T * N2);
     // UMMA operand strides (bytes)
     static constexpr int A1_SBO = 128, A1_LBO = MC1 * 128;
     static constexpr int B1_SBO = 128, B1_LBO = (N1 / 8) * 128;
     static constexpr int B2_SBO = 128, B2_LBO = (N2 / 8) * 128;
-    static constexpr int A2T_SBO = 128, A2T_LBO = (O / 8) * 128;
+    static constexpr int A2T_SBO = 128, A2T_LBO = MC2 * 128;
     // shared memory map (bytes from a 1024-aligned base)
     static constexpr int OFF_A2 = 0;
-    static constexpr int SZ_A2 = O * 128;
+    static constexpr int SZ_A2 = M2T * 128 * 128;
     static constexpr int OFF_A2T = OFF_A2 + SZ_A2;
-    static constexpr int SZ_A2T = (KT2 / 8) * (O / 8) * 128;
+    static constexpr int SZ_A2T = (KT2 / 8) * MC2 * 128;
     static constexpr int OFF_A1 = OFF_A2T + SZ_A2T;
     static constexpr int SZ_A1 = (K1 / 8) * MC1 * 128;
     static constexpr int OFF_B1 = OFF_A1 + SZ_A1;
@@ -83,10 +89,15 @@ struct IRTC {
     static constexpr int OFF_BN = OFF_W2P + SZ_W2P;
     static constexpr int SZ_BN = (4 * HID + 2 * COUT) * 4;
     static constexpr int OFF_BAR = (OFF_BN + SZ_BN + 15) / 16 * 16;
-    static constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;   // + slack for the 1024-byte alignment
+    static constexpr int OFF_COORD = OFF_BAR + 64;            // int[2][4]: (b, pi, pj) of the patch in flight
+    static constexpr int SMEM_BYTES = OFF_COORD + 32 + 1024;  // + slack for the 1024-byte alignment
+    // CTAs per SM: bounded by shared memory, TMEM columns and a 96-register budget per thread
+    static constexpr int CTAS = imax(1, (227 * 1024 / SMEM_BYTES) < (512 / TMEM_COLS) ? (227 * 1024 / SMEM_BYTES) : (512 / TMEM_COLS));
+    static constexpr int MINB = (CTAS * THREADS * 96 <= 65536) ? CTAS : imax(1, 65536 / (THREADS * 96));
     static_assert(HID % 4 == 0 && HID <= 68, "hidden width must be a multiple of 4 and at most 68");
     static_assert(TAILP <= 2, "at most two channel pairs in the K tail");
-    static_assert(M1T * N1 <= D2COL && D2COL + M2T * N2 <= TMEM_COLS, "TMEM budget");
+    static_assert(D2COL + M2T * N2 <= 512, "TMEM budget");
+    static_assert(PS_ == 8 || PS_ == 16, "patch size");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -109,7 +120,7 @@ __device__ __forceinline__ uint32_t pack_relu6(float lo, float hi) {
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, 1)
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
 patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -124,6 +135,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     uint64_t* bar_mma1 = bar_tma + 1;                     // [M1T] one per GEMM1 tile
     uint64_t* bar_mma2 = bar_mma1 + C::M1T;               // [M2T]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma2 + C::M2T);
+    volatile int* coord = reinterpret_cast<volatile int*>(sm + C::OFF_COORD);
 
     const uint32_t a1_addr = smem_u32(sm + C::OFF_A1), b1_addr = smem_u32(sm + C::OFF_B1);
     const uint32_t a2_addr = smem_u32(sm + C::OFF_A2), a2t_addr = smem_u32(sm + C::OFF_A2T);
@@ -147,7 +159,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     // constant-one channels that carry the BatchNorm shifts through the GEMMs
     {
         const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
-        for (int m = tid; m < C::O; m += C::THREADS) {            // A2: k = HID, every pixel
+        for (int m = tid; m < C::M2T * 128; m += C::THREADS) {    // A2: k = HID, every pixel row
             if (C::HID < 64) {
                 int off = m * 128 + ((((C::HID / 8) ^ (m & 7)) * 16) + (C::HID % 8) * 2);
                 *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A2 + off) = one;
@@ -166,13 +178,14 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     const int P = p.fh * p.fw;
     constexpr uint32_t X_BYTES = C::SZ_RAWX;
     constexpr uint32_t W_BYTES = (C::HP * 2 + 15) / 16 * 16;
-    auto issue_loads = [&](int patch) {         // one thread
+    auto issue_loads = [&](int patch, uint32_t slot) {         // one thread
         const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
+        coord[slot * 4 + 0] = b; coord[slot * 4 + 1] = pi; coord[slot * 4 + 2] = pj;   // published by the arrive below
         mbar_arrive_expect_tx(bar_tma, X_BYTES + (p.w_bulk ? W_BYTES : 0));
         tma_load_4d(rawX, &xmap, pj * C::PW - 8, pi * C::PH - 1, 0, b, bar_tma);
         if (p.w_bulk) bulk_g2s(rawW, p.w + (size_t)patch * p.w_row_stride, W_BYTES, bar_tma);
     };
-    if (tid == 0 && (int)blockIdx.x < p.total) issue_loads(blockIdx.x);
+    if (tid == 0 && (int)blockIdx.x < p.total) issue_loads(blockIdx.x, 0);
 
     constexpr uint32_t IDESC1 = idesc_bf16_f32(128, C::N1, false, false);
     constexpr uint32_t IDESC2 = idesc_bf16_f32(128, C::N2, false, false);
@@ -180,10 +193,10 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     uint32_t it = 0;
     for (int patch = blockIdx.x; patch < p.total; patch += gridDim.x, ++it) {
         const uint32_t par = it & 1;
-        const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
 
         // ---------------- P0: operands of this patch have landed ----------------
         mbar_wait(bar_tma, par);
+        const int b = coord[par * 4 + 0], pi = coord[par * 4 + 1], pj = coord[par * 4 + 2];
         if (!p.w_bulk) {
             const __nv_bfloat16* src = p.w + (size_t)patch * p.w_row_stride;
             for (int k = tid; k < C::HP; k += C::THREADS) rawW[k] = src[k];
@@ -304,7 +317,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                 umma_commit(bar_mma1 + t);          // epilogue of tile t can start while the next tile runs
             }
             const int next = patch + gridDim.x;
-            if (next < p.total) issue_loads(next);     // raw buffers were fully consumed in P1
+            if (next < p.total) issue_loads(next, par ^ 1);     // raw buffers were fully consumed in P1
         }
 
         // ---------------- P3: epilogue 1 (TMEM -> ReLU6 -> hidden tile) ----------------
@@ -371,7 +384,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
             bool tail = false;
             if (warp < C::PW) { if (lane < C::MAINP) { cp = lane; v = warp; } }
             else if (warp == C::PW && C::TAILP > 0) {
-                if ((lane % 2) < C::TAILP) { cp = 32 + (lane & 1); v = lane >> 1; tail = true; }
+                if ((lane % 2) < C::TAILP && (lane >> 1) < C::PW) { cp = 32 + (lane & 1); v = lane >> 1; tail = true; }
             }
             if (cp >= 0) {
                 __nv_bfloat162 wt[9];
@@ -423,7 +436,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
 #pragma unroll
                 for (int s = 0; s < C::K2 / 16; ++s) {
                     uint64_t da;
-                    if (s < 4) da = smem_desc(a2_addr + t * 128 * 128 + s * 32, 16, 1024, SWZ_128B);
+                    if (s < 4) da = smem_desc(a2_addr + t * 128 * 128 + s * 32, 16, 1024, SWZ_128B);   // K2 <= 64 or s < 4
                     else da = smem_desc(a2t_addr + 2 * (s - 4) * C::A2T_LBO + t * 16 * C::A2T_SBO, C::A2T_LBO, C::A2T_SBO, SWZ_NONE);
                     const uint64_t db = smem_desc(b2_addr + 2 * s * C::B2_LBO, C::B2_LBO, C::B2_SBO, SWZ_NONE);
                     umma_bf16(tmem + C::D2COL + t * C::N2, da, db, IDESC2, s > 0);
@@ -449,7 +462,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                 tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
-                    if (c0 + e < C::COUT) yp[(size_t)(c0 + e) * plane] = __float2bfloat16_rn(__uint_as_float(v[e]));
+                    if (c0 + e < C::COUT && m < C::O) yp[(size_t)(c0 + e) * plane] = __float2bfloat16_rn(__uint_as_float(v[e]));
             }
         }
         tc_fence_before_sync();
@@ -497,7 +510,7 @@ static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
     auto kern = patch_ir_tc_kernel<C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("patch_ir_tc attr: ") + cudaGetErrorString(e));
-    const int grid = std::min(p.total, std::max(1, device_sm_count()));
+    const int grid = std::min(p.total, std::max(1, device_sm_count()) * C::MINB);
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
     return check_launch("patch_ir_tc launch");
 }
@@ -507,7 +520,8 @@ int launch_patch_ir_tc(const void* x, const void* w, void* y, const float* const
     *handled = false;
     static const bool disabled = [] { const char* e = getenv("HSB_DISABLE_TC"); return e && e[0] == '1'; }();
     if (disabled || residual) return HSB_OK;
-    if (H / fh != 16 || W / fw != 16) return HSB_OK;
+    const int ps = H / fh;
+    if (W / fw != ps || (ps != 16 && ps != 8)) return HSB_OK;
     if ((W % 8) != 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return HSB_OK;      // TMA: 16-byte strides / base
     IRTCParams p;
     p.w = reinterpret_cast<const __nv_bfloat16*>(w);
@@ -518,14 +532,16 @@ int launch_patch_ir_tc(const void* x, const void* w, void* y, const float* const
     // bulk copies move ceil16(hp*2) bytes per row: the row (incl. that round-up) must stay inside its stride
     p.w_bulk = ((reinterpret_cast<uintptr_t>(w) & 15) == 0) && ((w_row_stride * 2) % 16 == 0) &&
                (((hp * 2 + 15) / 16 * 16) <= w_row_stride * 2);
-#define HSB_TC_CASE(CI, HD, CO)                                   \
-    if (Cin == CI && hid == HD && Cout == CO) {                   \
-        *handled = true;                                          \
-        return launch_tc<IRTC<CI, HD, CO>>(x, p, st);             \
+#define HSB_TC_CASE(CI, HD, CO, PS)                                           \
+    if (Cin == CI && hid == HD && Cout == CO && ps == PS) {                   \
+        *handled = true;                                                      \
+        return launch_tc<IRTC<CI, HD, CO, PS>>(x, p, st);                     \
     }
-    HSB_TC_CASE(34, 68, 19)      // HyperSeg-M level 4
-    HSB_TC_CASE(26, 52, 19)      // HyperSeg-S Cityscapes level 4
-    HSB_TC_CASE(22, 44, 12)      // HyperSeg-S CamVid level 4
+    HSB_TC_CASE(34, 68, 19, 16)     // HyperSeg-M level 4
+    HSB_TC_CASE(26, 52, 19, 16)     // HyperSeg-S Cityscapes level 4
+    HSB_TC_CASE(22, 44, 12, 16)     // HyperSeg-S CamVid level 4
+    HSB_TC_CASE(24, 48, 16, 8)      // HyperSeg-M / CamVid level 3
+    HSB_TC_CASE(14, 28, 8, 8)       // HyperSeg-S Cityscapes level 3
 #undef HSB_TC_CASE
     return HSB_OK;
 }

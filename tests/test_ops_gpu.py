@@ -258,16 +258,29 @@ def test_kernels_follow_the_current_stream():
 # ---------------------------------------------------------------------------------------------------------
 # tensor-core (tcgen05) path of the fused inverted-residual block: bf16, 16x16 patches, patch-major weights
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(34, 68, 19), (26, 52, 19), (22, 44, 12)])
+@pytest.mark.parametrize("shape", [(34, 68, 19, 16), (26, 52, 19, 16), (22, 44, 12, 16), (24, 48, 16, 8), (14, 28, 8, 8)])
 @pytest.mark.parametrize("grid", [(2, 3, 5), (1, 1, 1), (3, 1, 4), (1, 2, 1)])
 def test_ir_tensor_core_path(shape, grid):
-    """Every border case of the halo (corner / edge / interior / single patch) on the three shipped level-4 shapes."""
-    Cin, hid, Cout = shape
+    """Every border case of the halo (corner / edge / interior / single patch) on the shipped IR level shapes."""
+    Cin, hid, Cout, ps = shape
     B, fh, fw = grid
     hp = Cin * hid + 9 * hid + hid * Cout
-    x = _rand((B, Cin, fh * 16, fw * 16), 70).to(DEV, torch.bfloat16)
+    x = _rand((B, Cin, fh * ps, fw * ps), 70).to(DEV, torch.bfloat16)
     w = _rand((B, hp, fh, fw), 71, 0.3).to(DEV, torch.bfloat16)
     bns = [_bn(hid, 72), _bn(hid, 73), _bn(Cout, 74)]
+    ref = orc.patch_ir(x.float().cpu(), w.float().cpu(), hid, Cout, *bns)
+    y = ops.patch_ir(x, ops.weights_to_patch_major(w), hid, Cout, *[(a.to(DEV), b.to(DEV)) for a, b in bns])
+    assert rel_err(y.float().cpu(), ref) < BF16_TOL
+
+
+def test_ir_tensor_core_many_patches_per_cta():
+    """More patches than CTAs: exercises the persistent loop, barrier phases and the prefetch ring."""
+    Cin, hid, Cout, ps = 24, 48, 16, 8
+    B, fh, fw = 4, 16, 24            # 1536 patches
+    hp = Cin * hid + 9 * hid + hid * Cout
+    x = _rand((B, Cin, fh * ps, fw * ps), 80).to(DEV, torch.bfloat16)
+    w = _rand((B, hp, fh, fw), 81, 0.3).to(DEV, torch.bfloat16)
+    bns = [_bn(hid, 82), _bn(hid, 83), _bn(Cout, 84)]
     ref = orc.patch_ir(x.float().cpu(), w.float().cpu(), hid, Cout, *bns)
     y = ops.patch_ir(x, ops.weights_to_patch_major(w), hid, Cout, *[(a.to(DEV), b.to(DEV)) for a, b in bns])
     assert rel_err(y.float().cpu(), ref) < BF16_TOL
