@@ -33,6 +33,10 @@ SIGNATURES = {
     "hsb_signal2weights_fwd": [c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_void_p],
+    "hsb_head_packed_elems": [c_int, c_int, c_int],
+    "hsb_head_pack": [c_void_p, c_void_p, _F, c_int, c_int, c_int, c_int, c_void_p],
+    "hsb_signal2weights_packed_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int64, c_int64, c_int64, c_void_p],
     "hsb_patch_conv_fwd": [c_void_p, c_void_p, c_void_p, _F, _F, c_int,
                            c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                            c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -64,7 +68,7 @@ def load() -> ctypes.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.argtypes = argtypes
-        fn.restype = c_char_p if name == "hsb_last_error" else c_int
+        fn.restype = c_char_p if name == "hsb_last_error" else (c_int64 if name == "hsb_head_packed_elems" else c_int)
     _lib = lib
     return lib
 

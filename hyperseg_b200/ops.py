@@ -16,6 +16,9 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, HSB_BF16, HSB_F32, PAD_MODES, W_NCHW, W_PATCH_MAJOR
 
+import os
+
+_NO_TC_HEADS = os.environ.get("HSB_DISABLE_TC_HEADS", "0") == "1"
 _LAUNCHES = 0      # kernels launched through the C ABI by this process (each entry point launches exactly one)
 
 
@@ -170,6 +173,26 @@ def patch_ir(x, w, hidden, out_channels, bn1, bn2, bn3, residual=False):
     return y
 
 
+_PACKED_HEADS = {}      # (data_ptr, version, shape, groups) -> packed bf16 operand of a head's static weights
+
+
+def _packed_head(ws2d, sig_ch, groups):
+    key = (ws2d.data_ptr(), ws2d._version, tuple(ws2d.shape), groups, ws2d.dtype)
+    hit = _PACKED_HEADS.get(key)
+    if hit is not None:
+        return hit
+    n = _lib.load().hsb_head_packed_elems(sig_ch, ws2d.shape[0], groups)
+    if n <= 0:
+        raise ValueError("bad head dimensions")
+    packed = torch.empty(n, dtype=torch.bfloat16, device=ws2d.device)
+    _call("hsb_head_pack", ws2d.data_ptr(), packed.data_ptr(), None, sig_ch, ws2d.shape[0], groups,
+          _DTYPES[ws2d.dtype], _stream())
+    if len(_PACKED_HEADS) > 64:
+        _PACKED_HEADS.clear()
+    _PACKED_HEADS[key] = packed
+    return packed
+
+
 def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
     """Grouped 1x1 head: signal (B, C, fh, fw) -> logical (B, hp, fh, fw) weights in patch-major storage.
 
@@ -180,7 +203,8 @@ def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
     dt = _compute_dtype(s)
     if s.dtype != dt:
         s = s.to(dt)
-    ws = ws.detach().to(dt).reshape(ws.shape[0], -1).contiguous()
+    ws_src = ws.detach().reshape(ws.shape[0], -1)       # packed once per (tensor, version) on the tensor-core path
+    ws = ws_src.to(dt).contiguous()
     B, C, fh, fw = s.shape
     out_ch = ws.shape[0]
     if ws.shape[1] * groups != sig_ch:
@@ -194,6 +218,13 @@ def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
     sp = st[3] if fw > 1 else (st[2] if fh > 1 else 1)
     row = (hp + 7) // 8 * 8
     buf = torch.empty((B, fh, fw, row), dtype=dt, device=s.device)
+    if dt == torch.bfloat16 and (fh * fw) % 8 == 0 and sp == 1 and st[0] % 8 == 0 and st[1] % 8 == 0 \
+            and s.data_ptr() % 16 == 0 and (sig_ch // groups) <= 128 and not _NO_TC_HEADS:
+        # tensor-core path: static weights packed once into the UMMA operand layout
+        packed = _packed_head(ws_src if (ws_src.dtype in _DTYPES and ws_src.is_contiguous()) else ws, sig_ch, groups)
+        _call("hsb_signal2weights_packed_fwd", s.data_ptr(), packed.data_ptr(), buf.data_ptr(), B, sig_index, sig_ch,
+              out_ch, hp, groups, fh, fw, st[0], st[1], row, _stream())
+        return buf[..., :hp].permute(0, 3, 1, 2)
     _call("hsb_signal2weights_fwd", s.data_ptr(), ws.data_ptr(), buf.data_ptr(), B, sig_index, sig_ch, out_ch, hp, groups, fh, fw,
         st[0], st[1], sp, _DTYPES[dt], W_PATCH_MAJOR, row, _stream())
     return buf[..., :hp].permute(0, 3, 1, 2)

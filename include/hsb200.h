@@ -110,6 +110,25 @@ int hsb_signal2weights_fwd(const void* s, const void* ws, void* w_out,
                            int dtype, int out_layout, int64_t out_row_stride, void* stream);
 
 /*
+ * Tensor-core variant of the weight head for bf16 (tcgen05).  The static head weights are first packed, once,
+ * into the UMMA operand layout (K zero-padded to a multiple of 16, output channels tiled by 256 per group):
+ *   hsb_head_packed_elems  number of bf16 elements the packed buffer needs (-1 on bad dimensions)
+ *   hsb_head_pack          ws (out_ch, sig_ch/G) of `dtype` -> packed; row_scale (fp32, out_ch entries, may be NULL)
+ *                          multiplies each output channel's row, which lets an inference engine fold a BatchNorm
+ *                          scale that follows the dynamic convolution into the head
+ *   hsb_signal2weights_packed_fwd   same result as hsb_signal2weights_fwd with HSB_BF16 / HSB_W_PATCH_MAJOR.
+ * Requirements: s is bf16 with position stride 1 (NCHW), fh*fw % 8 == 0, 16-byte aligned base and strides.
+ * Replaces the same reference lines as hsb_signal2weights_fwd.
+ */
+int64_t hsb_head_packed_elems(int sig_ch, int out_ch, int groups);
+int hsb_head_pack(const void* ws, void* packed, const float* row_scale, int sig_ch, int out_ch, int groups,
+                  int dtype, void* stream);
+int hsb_signal2weights_packed_fwd(const void* s, const void* packed, void* w_out,
+                                  int B, int sig_index, int sig_ch, int out_ch, int hp, int groups,
+                                  int fh, int fw, int64_t s_stride_b, int64_t s_stride_c,
+                                  int64_t out_row_stride, void* stream);
+
+/*
  * General patch-wise convolution (any kernel size / groups / dilation, stride 1):
  *   tile = pad(x, (pad_h,pad_w), pad_mode)[b, :, i*ph : i*ph+ph+2*pad_h, j*pw : j*pw+pw+2*pad_w]
  *   y patch = valid_conv(tile, Wm),  Wm[o,c,ky,kx] = w_patch[((o*(Cin/G)+c)*kh+ky)*kw+kx]
