@@ -45,6 +45,9 @@ SIGNATURES = {
                             c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_void_p],
+    "hsb_decoder_input_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_int64, c_int64, c_int64, c_int64, c_int, c_void_p],
+    "hsb_upsample_argmax_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "hsb_weights_to_patch_major": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int, c_void_p],
 }
 

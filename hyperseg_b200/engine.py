@@ -116,14 +116,13 @@ class SegmentationEngine:
 
     def _forward_static(self):
         x = self.frames_dev.to(self.dtype)
-        if self.channels_last:
-            net = self.net
-            feats = net.backbone(x.contiguous(memory_format=torch.channels_last))
-            signal = net.weight_mapper(feats[-1])
-            self.logits = net.decoder([x] + [f.contiguous() for f in feats[:-1]], signal)
-        else:
-            self.logits = self.net(x)
-        self.labels = self.logits.argmax(1).to(torch.uint8)
+        net = self.net
+        xin = x.contiguous(memory_format=torch.channels_last) if self.channels_last else x
+        feats = net.backbone(xin)                  # NHWC feature maps are consumed as they are by the glue kernel
+        signal = net.weight_mapper(feats[-1])
+        self.logits = net.decoder.forward_features([x] + feats[:-1], signal)      # at the last decoder level's size
+        # final bilinear upsample + argmax fused: full-resolution logits are never written
+        self.labels = ops.upsample_argmax(self.logits, self.shape[-2:])
 
     @torch.no_grad()
     def step(self):
@@ -148,3 +147,14 @@ class SegmentationEngine:
             self.host_out.copy_(self.labels, non_blocking=True)
         self.stream.synchronize()
         return self.host_out
+
+    @torch.no_grad()
+    def full_logits(self) -> torch.Tensor:
+        """Logits of the last step at frame resolution (what model(frames) returns), computed on demand."""
+        import torch.nn.functional as F
+        with torch.cuda.stream(self.stream):
+            out = self.logits
+            if tuple(out.shape[-2:]) != tuple(self.shape[-2:]):
+                out = F.interpolate(out, self.shape[-2:], mode='bilinear', align_corners=False)
+        self.stream.synchronize()
+        return out

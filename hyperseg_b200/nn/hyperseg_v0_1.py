@@ -21,7 +21,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from .hyperseg_v1_0 import HyperGen as _HyperGenV10
-from .hyperseg_v1_0 import next_multiply
+from .hyperseg_v1_0 import assemble_level_input, next_multiply
 from .meta_patch import MetaPatchConv2d, make_meta_patch_conv2d_block
 from .meta_sequential import MetaSequential
 
@@ -239,14 +239,8 @@ class MultiScaleDecoder(nn.Module):
         p = None
         for level in range(len(x)):
             skip = x[-level - 1]
-            if p is None:
-                p = skip
-            else:
-                if p.shape[2:] != skip.shape[2:]:
-                    p = F.interpolate(p, skip.shape[2:], mode='bilinear', align_corners=False)
-                p = torch.cat((skip, p), dim=1)
-            coords = get_image_coordinates(p.shape[0], *p.shape[-2:], p.device)
-            p = torch.cat([coords.to(p.dtype), p], dim=1)
+            coords = get_image_coordinates(1, *skip.shape[-2:], skip.device)
+            p = assemble_level_input(coords, skip, p)
             p = getattr(self, f'level_{level}')(p, w[level])
         if self.out_fc is not None:
             p = self.out_fc(p, w[-1])

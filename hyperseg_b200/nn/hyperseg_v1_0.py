@@ -331,6 +331,21 @@ def divide_feature(in_feature, out_features, min_unit=8):
     return result
 
 
+def assemble_level_input(coords, skip, p):
+    """A decoder level's input: [coordinates | encoder feature | previous level, bilinearly upsampled]
+    (reference :235-240).  On the GPU this is one hsb_decoder_input_fwd launch; the stock PyTorch sequence is kept
+    for CPU tensors (the decoder itself has no CPU path -- this only serves host-side tests of the plumbing)."""
+    if skip.is_cuda and not (torch.is_grad_enabled() and (skip.requires_grad or (p is not None and p.requires_grad))):
+        return ops.decoder_input(coords, skip, p)
+    if p is not None:
+        if p.shape[2:] != skip.shape[2:]:
+            p = F.interpolate(p, skip.shape[2:], mode='bilinear', align_corners=False)
+        p = torch.cat((skip, p), dim=1)
+    else:
+        p = skip
+    return torch.cat([coords.expand(p.shape[0], -1, -1, -1).to(p.dtype), p], dim=1)
+
+
 class MultiScaleDecoder(nn.Module):
     """Coarse-to-fine decoder whose blocks are patch-wise dynamic layers (reference :94-253)."""
 
@@ -419,21 +434,20 @@ class MultiScaleDecoder(nn.Module):
         grid = cached if cached is not None else self._coordinate_grid(h, w, device)
         return grid.expand(b, -1, -1, -1)
 
-    def forward(self, x, s):
+    def forward_features(self, x, s):
+        """Everything but the final upsample to the frame resolution."""
         p = None
         for level in range(self.levels):
             skip = x[-level - 1]
-            if p is None:
-                p = skip
-            else:
-                if p.shape[2:] != skip.shape[2:]:
-                    p = F.interpolate(p, skip.shape[2:], mode='bilinear', align_corners=False)
-                p = torch.cat((skip, p), dim=1)
-            coords = self.get_image_coordinates(p.shape[0], *p.shape[-2:], p.device)
-            p = torch.cat([coords.to(p.dtype), p], dim=1)
+            coords = self.get_image_coordinates(1, *skip.shape[-2:], skip.device)
+            p = assemble_level_input(coords, skip, p)
             p = getattr(self, f'level_{level}')(p, s)
         if self.out_fc is not None:
             p = self.out_fc(p, s)
+        return p
+
+    def forward(self, x, s):
+        p = self.forward_features(x, s)
         if p.shape[2:] != x[0].shape[2:]:
             p = F.interpolate(p, x[0].shape[2:], mode='bilinear', align_corners=False)
         return p

@@ -17,7 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from .hyperseg_v1_0 import (HyperPatch, HyperPatchConv2d, HyperPatchInvertedResidual, HyperPatchNoPadding,  # noqa: F401
+from .hyperseg_v1_0 import (assemble_level_input, HyperPatch, HyperPatchConv2d, HyperPatchInvertedResidual, HyperPatchNoPadding,  # noqa: F401
                             WeightMapper, divide_feature, make_hyper_patch_conv2d_block, next_multiply)
 from .hyperseg_v1_0 import HyperGen as _HyperGenV10
 from .hyperseg_v1_0 import MultiScaleDecoder as _DecoderV10
@@ -149,19 +149,13 @@ class MultiScaleDecoder(nn.Module):
     _coordinate_grid = staticmethod(_DecoderV10._coordinate_grid)
     get_image_coordinates = _DecoderV10.get_image_coordinates
 
-    def forward(self, x, s):
+    def forward_features(self, x, s):
         p = None
         w = None
         for level in range(self.levels):
             skip = x[-level - 1]
-            if p is None:
-                p = skip
-            else:
-                if p.shape[2:] != skip.shape[2:]:
-                    p = F.interpolate(p, skip.shape[2:], mode='bilinear', align_corners=False)
-                p = torch.cat((skip, p), dim=1)
-            coords = self.get_image_coordinates(p.shape[0], *p.shape[-2:], p.device)
-            p = torch.cat([coords.to(p.dtype), p], dim=1)
+            coords = self.get_image_coordinates(1, *skip.shape[-2:], skip.device)
+            p = assemble_level_input(coords, skip, p)
             block = self.level_blocks[level]
             if level < self.unify_level - 1:
                 p = block(p, self.weight_blocks[level](s))
@@ -172,6 +166,10 @@ class MultiScaleDecoder(nn.Module):
                 p = block(p, w[:, self._ranges[i]:self._ranges[i + 1]])
         if self.out_fc is not None:
             p = self.out_fc(p, s)
+        return p
+
+    def forward(self, x, s):
+        p = self.forward_features(x, s)
         if p.shape[2:] != x[0].shape[2:]:
             p = F.interpolate(p, x[0].shape[2:], mode='bilinear', align_corners=False)
         return p

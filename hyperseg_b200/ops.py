@@ -280,3 +280,44 @@ def weights_to_patch_major(w):
     buf = torch.empty((B, fh, fw, row), dtype=w.dtype, device=w.device)
     _call("hsb_weights_to_patch_major", w.data_ptr(), buf.data_ptr(), B, hp, fh, fw, row, _DTYPES[w.dtype], _stream())
     return buf[..., :hp].permute(0, 3, 1, 2)
+
+
+def decoder_input(coords, feature, prev):
+    """cat(coords, feature, bilinear_upsample(prev, feature.shape[-2:])) in one kernel.
+
+    ``coords`` is (1 or B, 2, H, W) (broadcast over the batch) or None, ``feature`` (B, Cf, H, W) in any memory
+    format, ``prev`` (B, Cp, h, w) or None."""
+    _require_cuda(feature, prev, coords)
+    _require_inference(feature, prev)
+    dt = _compute_dtype(feature)
+    B, Cf, H, W = feature.shape
+    if feature.dtype != dt:
+        feature = feature.to(dt)
+    Cc = Cp = 0
+    h = w = 1
+    cptr = pptr = None
+    if coords is not None:
+        coords = coords[:1].to(dt).contiguous()
+        Cc, cptr = coords.shape[1], coords.data_ptr()
+    if prev is not None:
+        prev = prev.to(dt).contiguous()
+        Cp, h, w, pptr = prev.shape[1], prev.shape[2], prev.shape[3], prev.data_ptr()
+    out = torch.empty((B, Cc + Cf + Cp, H, W), dtype=dt, device=feature.device)
+    st = feature.stride()
+    _call("hsb_decoder_input_fwd", cptr, feature.data_ptr(), pptr, out.data_ptr(), B, Cc, Cf, Cp, H, W, h, w,
+          st[0], st[1], st[2], st[3], _DTYPES[dt], _stream())
+    return out
+
+
+def upsample_argmax(logits, size):
+    """uint8 label map = argmax over classes of the bilinearly upsampled logits (never materialised)."""
+    _require_cuda(logits)
+    dt = logits.dtype
+    if dt not in _DTYPES:
+        raise TypeError(f"unsupported dtype {dt}")
+    logits = logits.contiguous()
+    B, C, h, w = logits.shape
+    H, W = size
+    labels = torch.empty((B, H, W), dtype=torch.uint8, device=logits.device)
+    _call("hsb_upsample_argmax_fwd", logits.data_ptr(), labels.data_ptr(), B, C, h, w, H, W, _DTYPES[dt], _stream())
+    return labels

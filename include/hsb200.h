@@ -154,6 +154,28 @@ int hsb_meta_conv2d_fwd(const void* x, const void* w, void* y,
                         int pad_mode, int dtype, void* stream);
 
 /*
+ * Decoder glue, one pass: out = cat(coords, feature, bilinear_upsample(prev, (H, W)))  along channels.
+ *   coords  (1, Cc, H, W) contiguous, broadcast over the batch (may be NULL with Cc == 0)
+ *   feature (B, Cf, H, W) with arbitrary element strides (NCHW or NHWC)
+ *   prev    (B, Cp, h, w) contiguous NCHW, upsampled as F.interpolate(mode='bilinear', align_corners=False)
+ *   out     (B, Cc+Cf+Cp, H, W) contiguous NCHW
+ * Replaces F.interpolate + torch.cat + torch.cat at hyperseg/models/hyperseg_v1_0.py:235-240
+ * (hyperseg_v1_0_unify.py:234-240, hyperseg_v0_1.py:187-194).
+ */
+int hsb_decoder_input_fwd(const void* coords, const void* feature, const void* prev, void* out,
+                          int B, int Cc, int Cf, int Cp, int H, int W, int h, int w,
+                          int64_t f_stride_b, int64_t f_stride_c, int64_t f_stride_y, int64_t f_stride_x,
+                          int dtype, void* stream);
+
+/*
+ * Segmentation tail when only labels are wanted: labels[b,y,x] = argmax_c bilinear_upsample(logits)[b,c,y,x]
+ * (uint8).  Replaces the final F.interpolate (hyperseg/models/hyperseg_v1_0.py:250-251) followed by
+ * output.argmax(1) (hyperseg/test.py:171); the full-resolution logits are never written.
+ */
+int hsb_upsample_argmax_fwd(const void* logits, void* labels, int B, int C, int h, int w, int H, int W,
+                            int dtype, void* stream);
+
+/*
  * Layout change (B, hp, fh, fw) -> (B, fh, fw, row_stride) for weights handed over in the
  * reference layout.  Replaces weight.permute(0,2,3,1).reshape(...) at
  * hyperseg/models/hyperseg_v1_0.py:345-347, :492-493, :549.

@@ -284,3 +284,61 @@ def test_ir_tensor_core_many_patches_per_cta():
     ref = orc.patch_ir(x.float().cpu(), w.float().cpu(), hid, Cout, *bns)
     y = ops.patch_ir(x, ops.weights_to_patch_major(w), hid, Cout, *[(a.to(DEV), b.to(DEV)) for a, b in bns])
     assert rel_err(y.float().cpu(), ref) < BF16_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------
+# decoder glue kernels against the stock PyTorch sequence they replace
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("geom", [(2, 16, 16, 128, 256, 64, 128), (1, 3, 7, 37, 52, 19, 26), (2, 10, 0, 16, 32, 1, 1),
+                                  (1, 6, 5, 24, 40, 24, 40)])
+def test_decoder_input_matches_interpolate_cat(geom, dtype):
+    import torch.nn.functional as F
+    B, Cf, Cp, H, W, h, w = geom
+    feat = _rand((B, Cf, H, W), 90).to(DEV, dtype)
+    prev = _rand((B, Cp, h, w), 91).to(DEV, dtype) if Cp else None
+    xs, ys = torch.linspace(-1, 1, W), torch.linspace(-1, 1, H)
+    coords = torch.stack((xs.view(1, W).expand(H, W), ys.view(H, 1).expand(H, W)), 0).unsqueeze(0).to(DEV, dtype)
+    parts = [coords.expand(B, -1, -1, -1), feat]
+    if Cp:
+        parts.append(F.interpolate(prev, (H, W), mode="bilinear", align_corners=False) if (h, w) != (H, W) else prev)
+    ref = torch.cat(parts, 1)
+    for f in (feat, feat.contiguous(memory_format=torch.channels_last)):
+        out = ops.decoder_input(coords, f, prev)
+        assert out.shape == ref.shape and out.dtype == dtype and out.is_contiguous()
+        tol = 1e-6 if dtype == torch.float32 else 8e-3          # one bf16 ulp on the interpolated channels
+        assert (out.float() - ref.float()).abs().max().item() <= tol * max(1.0, ref.float().abs().max().item())
+        assert torch.equal(out[:, :2 + Cf], ref[:, :2 + Cf])     # copied channels are bit-exact
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("geom", [(2, 19, 64, 128, 128, 256), (1, 12, 33, 20, 66, 40), (1, 5, 16, 16, 16, 16), (1, 21, 9, 7, 31, 23)])
+def test_upsample_argmax_matches_interpolate_argmax(geom, dtype):
+    import torch.nn.functional as F
+    B, C, h, w, H, W = geom
+    logits = _rand((B, C, h, w), 95).to(DEV, dtype)
+    full = F.interpolate(logits, (H, W), mode="bilinear", align_corners=False) if (h, w) != (H, W) else logits
+    ref = full.argmax(1)
+    labels = ops.upsample_argmax(logits, (H, W))
+    assert labels.dtype == torch.uint8 and labels.shape == (B, H, W)
+    agree = (labels.long() == ref).float().mean().item()
+    # ties / last-ulp differences of the interpolation may flip a label between two near-equal classes
+    top2 = full.float().topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    hard = (labels.long() != ref) & (margin > (1e-5 if dtype == torch.float32 else 4e-2))
+    assert agree > 0.99 and not hard.any()
+
+
+def test_engine_labels_match_model_argmax():
+    from hyperseg_b200.engine import SegmentationEngine
+    from hyperseg_b200.synthetic import build_model, synthetic_frames
+    model = build_model("hyperseg-m", seed=0)
+    frames = synthetic_frames(2, 64, 128).pin_memory()
+    for graph in (False, True):
+        eng = SegmentationEngine(model, 2, 64, 128, use_graph=graph)
+        labels = eng(frames).clone()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            ref = model.cuda()(frames.cuda()).argmax(1).cpu()
+        agree = (labels.long() == ref).float().mean().item()
+        assert agree > 0.97, agree                        # bf16 engine vs autocast reference path
+        assert eng.launches_per_step >= 16                # 5 heads + 5 patch kernels + 5 glue + tail, all ours
