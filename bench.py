@@ -308,6 +308,23 @@ def run_ours(args):
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - e2e_start)
 
+    # ---- whole-box result (outside the timed regions): NCCL all-reduce of the confusion matrix ----
+    whole_box = None
+    if world > 1:
+        from hyperseg_b200 import dist as hdist
+        ncls = 19
+        pred = engine.labels
+        target = torch.roll(pred, shifts=1, dims=-1)                 # synthetic "ground truth" of the right shape
+        local_mat = hdist.confusion_matrix(pred, target, ncls)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a0.record()
+        total_mat = hdist.all_reduce_confusion(local_mat.clone())
+        a1.record()
+        torch.cuda.synchronize()
+        whole_box = {"miou": hdist.miou(total_mat)[0], "confusion_allreduce_ms": a0.elapsed_time(a1),
+                     "pixels": int(total_mat.sum().item())}
+
     times = torch.tensor([dev_ms, e2e_ms, wall_ms], device=f"cuda:{local}", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -353,7 +370,7 @@ def run_ours(args):
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "bytes_per_launch": top["bytes"],
                          "ms_per_launch": top["ms"]},
-            "patch_conv": agg(conv_keys), "heads": agg(head_keys),
+            "patch_conv": agg(conv_keys), "heads": agg(head_keys), "whole_box": whole_box,
             "kernels": {k: {"ms": round(v["ms"], 5), "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)}
                         for k, v in roof.items()},
         }
