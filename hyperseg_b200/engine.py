@@ -119,7 +119,7 @@ class SegmentationEngine:
         net = self.net
         xin = x.contiguous(memory_format=torch.channels_last) if self.channels_last else x
         feats = net.backbone(xin)                  # NHWC feature maps are consumed as they are by the glue kernel
-        signal = net.weight_mapper(feats[-1])
+        signal = net.weight_mapper(feats[-1]).contiguous()      # NCHW once: every head reads position-contiguous rows
         self.logits = net.decoder.forward_features([x] + feats[:-1], signal)      # at the last decoder level's size
         # final bilinear upsample + argmax fused: full-resolution logits are never written
         self.labels = ops.upsample_argmax(self.logits, self.shape[-2:])

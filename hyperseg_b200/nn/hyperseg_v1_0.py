@@ -11,8 +11,9 @@ dynamic layers *do*:
                                           (reference :328-376 = pad, unfold, 3 grouped convs, 3 BN, 2 ReLU6, re-tile)
   HyperPatchConv2d.forward             -> hsb_signal2weights_fwd + hsb_patch_conv_fwd (reference :543-557)
 
-The backbone, the WeightMapper trunk and the decoder glue (upsample / concat / coordinates) are stock
-PyTorch, as in the reference.
+The backbone and the WeightMapper trunk are stock PyTorch, as in the reference; the decoder glue (bilinear upsample
+of the previous level + concat with the encoder feature and the coordinate channels, reference :235-240) is one
+hsb_decoder_input_fwd launch per level on the GPU.
 """
 import numbers
 from functools import partial

@@ -212,10 +212,12 @@ def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
     if sig_index + sig_ch > C:
         raise ValueError(f"signal slice [{sig_index}, {sig_index + sig_ch}) exceeds {C} signal channels")
     st = s.stride()
-    if fh > 1 and fw > 1 and st[2] != fw * st[3]:
+    sp = st[3] if fw > 1 else (st[2] if fh > 1 else 1)
+    if (fh > 1 and fw > 1 and st[2] != fw * st[3]) or (dt == torch.bfloat16 and sp != 1 and not _NO_TC_HEADS):
+        # the tensor-core head wants position-contiguous (NCHW) signal rows; the signal map is small (1/32 resolution)
         s = s.contiguous()
         st = s.stride()
-    sp = st[3] if fw > 1 else (st[2] if fh > 1 else 1)
+        sp = st[3] if fw > 1 else (st[2] if fh > 1 else 1)
     row = (hp + 7) // 8 * 8
     buf = torch.empty((B, fh, fw, row), dtype=dt, device=s.device)
     if dt == torch.bfloat16 and (fh * fw) % 8 == 0 and sp == 1 and st[0] % 8 == 0 and st[1] % 8 == 0 \
