@@ -6,11 +6,11 @@
 //
 //   * the static head weights are packed ONCE (hsb_head_pack) into the UMMA K-major operand layout, zero padded
 //     to K % 16 == 0 and to 256-channel tiles, so a tile of B is one cp.async.bulk;
-//   * a CTA owns 128 consecutive positions of one group: the signal slab [K x 128] is copied from NCHW straight
-//     into the MN-major operand layout (16-byte units of 8 positions -- no transposition), then the CTA walks the
-//     group's output-channel tiles: warp 4 streams B tiles (2-stage ring) and issues 128x256xK MMAs into a
-//     2-stage TMEM accumulator; warps 0-3 drain TMEM -> bf16 -> a shared staging tile -> coalesced row stores,
-//     overlapping the next tile's MMA.
+//   * a CTA owns 128 consecutive positions and a contiguous range of (group, 256-channel tile) items: the producer
+//     warp copies the item's signal slab [K x 128] from NCHW straight into the MN-major operand layout (16-byte
+//     units of 8 positions -- no transposition), streams the packed B tile (2-stage operand ring) and issues
+//     128x256xK MMAs into a 2-stage TMEM accumulator; eight epilogue warps drain TMEM -> bf16 -> a shared staging
+//     tile -> coalesced row stores, one item behind the MMAs.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -18,7 +18,8 @@ namespace hsb {
 
 constexpr int HD_NT = 256;                 // output channels per tile
 constexpr int HD_M = 128;                  // positions per CTA
-constexpr int HD_THREADS = 160;            // 4 epilogue warps + 1 producer/MMA warp
+constexpr int HD_EPI_WARPS = 8;            // 4 TMEM quadrants x 2 column halves
+constexpr int HD_THREADS = 32 * (HD_EPI_WARPS + 1);     // + 1 producer / MMA warp
 constexpr int HD_STAGE_PITCH = HD_NT * 2 + 16;
 
 struct HeadTCParams {
@@ -28,17 +29,23 @@ struct HeadTCParams {
     int NTOT;                         // B * P positions
     int P;
     int sig_index, spg, kpad, opg, hp, groups, otiles;
+    int items;                        // groups * otiles work items per position tile
+    int splits;                       // CTAs sharing one position tile
     int64_t ssb, ssc;                 // signal strides (elements); position stride is 1
     int64_t row_stride;               // output row stride (elements)
 };
 
 __host__ __device__ inline size_t head_smem_bytes(int kpad) {
-    size_t a = (size_t)kpad * HD_M * 2;                 // A operand
+    size_t a = 2 * (size_t)kpad * HD_M * 2;             // two A stages (signal slab of the item's group)
     size_t b = 2 * (size_t)HD_NT * kpad * 2;            // two B stages
     size_t st = (size_t)HD_M * HD_STAGE_PITCH;          // output staging
     return a + b + st + 128 + 1024;
 }
 
+// A CTA owns 128 positions and a contiguous range of (group, channel-tile) items.  Warp 8 is the producer: it copies
+// the item's signal slab into the MN-major A operand (all 32 lanes), streams the packed B tile with cp.async.bulk and
+// issues the MMAs (lane 0) into a two-stage TMEM accumulator.  Warps 0-7 drain: quadrant = warp % 4, column half =
+// warp / 4; TMEM -> bf16 -> staging rows -> coalesced stores, one item behind the MMAs.
 __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const HeadTCParams p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -46,94 +53,102 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
     const int kpad = p.kpad;
     const size_t a_bytes = (size_t)kpad * HD_M * 2, b_bytes = (size_t)HD_NT * kpad * 2;
     unsigned char* a_sm = sm;
-    unsigned char* b_sm = a_sm + a_bytes;
+    unsigned char* b_sm = a_sm + 2 * a_bytes;
     unsigned char* st_sm = b_sm + 2 * b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(st_sm + (size_t)HD_M * HD_STAGE_PITCH);
-    uint64_t* b_full = bars;          // [2]
-    uint64_t* b_empty = bars + 2;     // [2]
-    uint64_t* d_full = bars + 4;      // [2]
-    uint64_t* d_empty = bars + 6;     // [2]
+    uint64_t* b_full = bars;          // [2] B tile landed
+    uint64_t* s_empty = bars + 2;     // [2] operand stage (A and B) consumed by the tensor core
+    uint64_t* d_full = bars + 4;      // [2] accumulator ready
+    uint64_t* d_empty = bars + 6;     // [2] accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-    const int g = blockIdx.y;
     const int n0 = blockIdx.x * HD_M;
+    const int per = (p.items + p.splits - 1) / p.splits;
+    const int it0 = blockIdx.y * per, it1 = min(p.items, it0 + per);
+    const int nitems = it1 - it0;
+    if (nitems <= 0) return;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(b_full + i, 1);
-            mbar_init(b_empty + i, 1);
+            mbar_init(s_empty + i, 1);
             mbar_init(d_full + i, 1);
-            mbar_init(d_empty + i, 4);          // one arrive per epilogue warp
+            mbar_init(d_empty + i, HD_EPI_WARPS);
         }
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, 512);
-
-    // ---- signal slab -> A operand (MN-major, no swizzle): unit(mc, k) = (k/8)*LBO + mc*128 + (k%8)*16 ----
-    const int a_lbo = (HD_M / 8) * 128;
-    for (int i = tid; i < kpad * (HD_M / 8); i += HD_THREADS) {
-        const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
-        const int n = n0 + mc * 8;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (k < p.spg && n < p.NTOT) {
-            const int b = n / p.P, pp = n % p.P;          // 8 consecutive positions never straddle images (P % 8 == 0)
-            v = *reinterpret_cast<const uint4*>(p.s + (size_t)b * p.ssb + (size_t)(p.sig_index + g * p.spg + k) * p.ssc + pp);
-        }
-        *reinterpret_cast<uint4*>(a_sm + (k >> 3) * a_lbo + mc * 128 + (k & 7) * 16) = v;
-    }
-    fence_proxy_async_smem();
+    if (warp == HD_EPI_WARPS) tmem_alloc(tmem_slot, 512);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+    const int a_lbo = (HD_M / 8) * 128, b_lbo = (HD_NT / 8) * 128;
 
-    const int ntiles = p.otiles;
-    const int b_lbo = (HD_NT / 8) * 128;
-
-    if (warp == 4) {
-        if (lane == 0) {
-            const uint32_t idesc = idesc_bf16_f32(HD_M, HD_NT, /*A MN-major*/ true, false);
-            const uint32_t a_addr = smem_u32(a_sm);
-            const __nv_bfloat16* src = p.packed + (size_t)g * ntiles * HD_NT * kpad;
-            // prologue: first B tile
-            mbar_arrive_expect_tx(b_full, (uint32_t)b_bytes);
-            bulk_g2s(b_sm, src, (uint32_t)b_bytes, b_full);
-            for (int t = 0; t < ntiles; ++t) {
-                const int st = t & 1;
-                if (t + 1 < ntiles) {                         // prefetch the next B tile into the other stage
-                    const int ns = (t + 1) & 1;
-                    if (t + 1 >= 2) mbar_wait(b_empty + ns, ((t + 1) / 2 - 1) & 1);
-                    mbar_arrive_expect_tx(b_full + ns, (uint32_t)b_bytes);
-                    bulk_g2s(b_sm + ns * b_bytes, src + (size_t)(t + 1) * HD_NT * kpad, (uint32_t)b_bytes, b_full + ns);
+    if (warp == HD_EPI_WARPS) {
+        // ================= producer / MMA warp =================
+        const uint32_t idesc = idesc_bf16_f32(HD_M, HD_NT, /*A MN-major*/ true, false);
+        int stage_group0 = -1, stage_group1 = -1;
+        auto stage_operands = [&](int j) {          // whole warp: A slab (if the group changed) + B tile of item j
+            const int st = j & 1, it = it0 + j, g = it / p.otiles, t = it % p.otiles;
+            if (j >= 2) mbar_wait(s_empty + st, ((j >> 1) - 1) & 1);      // MMAs of item j-2 done with this stage
+            if ((st ? stage_group1 : stage_group0) != g) {
+                unsigned char* a_dst = a_sm + st * a_bytes;
+                // unit(mc, k) = (k/8)*LBO + mc*128 + (k%8)*16: 8 consecutive positions of signal channel k
+                for (int i = lane; i < kpad * (HD_M / 8); i += 32) {
+                    const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
+                    const int n = n0 + mc * 8;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (k < p.spg && n < p.NTOT) {
+                        const int b = n / p.P, pp = n % p.P;          // P % 8 == 0: a unit never straddles images
+                        v = *reinterpret_cast<const uint4*>(p.s + (size_t)b * p.ssb +
+                                                            (size_t)(p.sig_index + g * p.spg + k) * p.ssc + pp);
+                    }
+                    *reinterpret_cast<uint4*>(a_dst + (k >> 3) * a_lbo + mc * 128 + (k & 7) * 16) = v;
                 }
-                mbar_wait(b_full + st, (t / 2) & 1);
-                if (t >= 2) mbar_wait(d_empty + st, (t / 2 - 1) & 1);      // epilogue drained this accumulator
+                if (st) stage_group1 = g; else stage_group0 = g;
+                fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(b_full + st, (uint32_t)b_bytes);
+                bulk_g2s(b_sm + st * b_bytes, p.packed + ((size_t)g * p.otiles + t) * HD_NT * kpad, (uint32_t)b_bytes,
+                         b_full + st);
+            }
+        };
+        stage_operands(0);
+        for (int j = 0; j < nitems; ++j) {
+            const int st = j & 1;
+            if (j + 1 < nitems) stage_operands(j + 1);          // overlaps the MMAs / epilogue of item j
+            if (lane == 0) {
+                mbar_wait(b_full + st, (j >> 1) & 1);
+                if (j >= 2) mbar_wait(d_empty + st, ((j >> 1) - 1) & 1);      // epilogue drained this accumulator
                 tc_fence_after_sync();
-                const uint32_t b_addr = smem_u32(b_sm + st * b_bytes);
+                const uint32_t a_addr = smem_u32(a_sm + st * a_bytes), b_addr = smem_u32(b_sm + st * b_bytes);
                 for (int s = 0; s < kpad / 16; ++s) {
                     const uint64_t da = smem_desc(a_addr + 2 * s * a_lbo, a_lbo, 128, SWZ_NONE);
                     const uint64_t db = smem_desc(b_addr + 2 * s * b_lbo, b_lbo, 128, SWZ_NONE);
                     umma_bf16(tmem + st * HD_NT, da, db, idesc, s > 0);
                 }
                 umma_commit(d_full + st);       // accumulator ready
-                umma_commit(b_empty + st);      // B stage reusable
+                umma_commit(s_empty + st);      // operand stage reusable
             }
+            __syncwarp();
         }
     } else {
-        // ---- epilogue warps: quadrant q of the accumulator = rows 32q .. 32q+31 ----
-        const int q = warp;
+        // ================= epilogue warps =================
+        const int q = warp & 3, half = warp >> 2;
         const int row = q * 32 + lane;
-        unsigned char* my_row = st_sm + (size_t)row * HD_STAGE_PITCH;
-        for (int t = 0; t < ntiles; ++t) {
-            const int st = t & 1;
-            mbar_wait(d_full + st, (t / 2) & 1);
-            tc_fence_after_sync();
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + st * HD_NT;
+        constexpr int HC = HD_NT / 2;                     // columns per warp
+        unsigned char* my_row = st_sm + (size_t)row * HD_STAGE_PITCH + half * HC * 2;
+        for (int j = 0; j < nitems; ++j) {
+            const int st = j & 1, it = it0 + j, g = it / p.otiles, t = it % p.otiles;
             const int o_base = g * p.opg + t * HD_NT;
             const int o_end = min(min((g + 1) * p.opg, p.hp), o_base + HD_NT);
-            const int nvalid = o_end - o_base;                   // may be <= 0 for a fully padded tile
-            const int ncols = min(HD_NT, (max(nvalid, 0) + 31) & ~31);
-#pragma unroll 2
+            const int nvalid = max(o_end - o_base, 0) - half * HC;      // valid columns in this warp's half
+            const int ncols = min(HC, (max(nvalid, 0) + 31) & ~31);
+            mbar_wait(d_full + st, (j >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + st * HD_NT + half * HC;
             for (int c = 0; c < ncols; c += 32) {
                 uint32_t v0[16], v1[16];
                 tmem_ld16(taddr + c, v0);
@@ -156,14 +171,15 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(d_empty + st);          // TMEM stage free again
-            // coalesced write-out of this warp's 32 rows
+            // coalesced write-out of this warp's 32 rows x its column half
             if (nvalid > 0) {
-                const bool pairs = (o_base & 1) == 0;
+                const int ob = o_base + half * HC;
+                const bool pairs = (ob & 1) == 0;
                 for (int r = 0; r < 32; ++r) {
                     const int n = n0 + q * 32 + r;
                     if (n >= p.NTOT) break;
-                    const unsigned char* srow = st_sm + (size_t)(q * 32 + r) * HD_STAGE_PITCH;
-                    __nv_bfloat16* drow = p.out + (size_t)n * p.row_stride + o_base;
+                    const unsigned char* srow = st_sm + (size_t)(q * 32 + r) * HD_STAGE_PITCH + half * HC * 2;
+                    __nv_bfloat16* drow = p.out + (size_t)n * p.row_stride + ob;
                     if (pairs) {
                         for (int c = lane * 2; c < nvalid; c += 64) {
                             if (c + 1 < nvalid) *reinterpret_cast<uint32_t*>(drow + c) = *reinterpret_cast<const uint32_t*>(srow + c * 2);
@@ -174,12 +190,12 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                     }
                 }
             }
-            __syncwarp();       // staging rows are rewritten by the next tile
+            __syncwarp();       // staging rows are rewritten by the next item
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, 512);
+    if (warp == HD_EPI_WARPS) tmem_dealloc(tmem, 512);
 }
 
 // ---- packing of the static head weights into the UMMA operand layout ---------------------------------------------------
@@ -256,10 +272,21 @@ extern "C" int hsb_signal2weights_packed_fwd(const void* s, const void* packed, 
     p.ssb = s_stride_b; p.ssc = s_stride_c; p.row_stride = out_row_stride;
     const size_t smem = head_smem_bytes(p.kpad);
     HSB_REQUIRE(smem <= 227 * 1024, HSB_ERR_UNSUPPORTED, "signal2weights_packed: sig_ch / groups too large for one CTA");
-    HSB_REQUIRE(groups <= 65535, HSB_ERR_UNSUPPORTED, "signal2weights_packed: too many groups");
     cudaError_t e = cudaFuncSetAttribute(signal2weights_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("signal2weights_packed attr: ") + cudaGetErrorString(e));
-    dim3 grid(ceil_div(p.NTOT, HD_M), groups);
+    p.items = groups * p.otiles;
+    const int tiles = ceil_div(p.NTOT, HD_M);
+    // split the items of a position tile over `splits` CTAs so that (waves of CTAs) x (items per CTA) is smallest;
+    // ties go to fewer, longer-running CTAs (the per-CTA set-up -- TMEM allocation, barriers -- is not free)
+    const int sms = std::max(1, device_sm_count());
+    int splits = 1, best = ceil_div(tiles, sms) * p.items;
+    for (int sp = 2; sp <= p.items; ++sp) {
+        const int cost = ceil_div(tiles * sp, sms) * ceil_div(p.items, sp);
+        if (cost < best) { best = cost; splits = sp; }
+    }
+    p.splits = splits;
+    HSB_REQUIRE(splits <= 65535, HSB_ERR_UNSUPPORTED, "signal2weights_packed: grid too large");
+    dim3 grid(tiles, splits);
     signal2weights_tc_kernel<<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
     return check_launch("signal2weights_packed launch");
 }
