@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             const int st = j & 1, it = it0 + j, g = it / p.otiles, t = it % p.otiles;
             const int o_base = g * p.opg + t * HD_NT;
             const int o_end = min(min((g + 1) * p.opg, p.hp), o_base + HD_NT);
-            const int nvalid = max(o_end - o_base, 0) - half * HC;      // valid columns in this warp's half
+            const int nvalid = min(HC, max(o_end - o_base, 0) - half * HC);   // valid columns in this warp's half (may be <= 0)
             const int ncols = min(HC, (max(nvalid, 0) + 31) & ~31);
             mbar_wait(d_full + st, (j >> 1) & 1);
             tc_fence_after_sync();
