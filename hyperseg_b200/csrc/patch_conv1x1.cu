@@ -216,12 +216,15 @@ template <typename T>
 static int dispatch_1x1(Conv1x1Params& p, cudaStream_t st) {
     const size_t es = sizeof(T);
     const int pix = p.ph * p.pw;
-    // patches per CTA: enough pixels to keep 128 threads busy, bounded by ~44 KB of shared memory
+    // patches per CTA: at most ~44 KB of shared memory (several CTAs per SM overlap load and compute), a divisor
+    // of fw when one is close, and small enough that the grid has >= 4 CTAs per SM
     const size_t per_patch = (size_t)p.wrow_smem * es + (size_t)p.Cin * pix * es;
     int PG = (int)std::max<size_t>(1, (44 * 1024) / per_patch);
     PG = std::min(PG, p.fw);
     PG = std::min(PG, 32);
-    // prefer a PG that divides fw (no ragged last CTA) when one is close
+    const int64_t rows = (int64_t)p.B * p.fh;
+    const int64_t want = 4LL * std::max(1, device_sm_count());
+    while (PG > 1 && rows * ceil_div(p.fw, PG) < want) --PG;
     for (int cand = PG; cand >= std::max(1, PG / 2); --cand)
         if (p.fw % cand == 0) { PG = cand; break; }
     int PB = ((PG * p.pw) % 2 == 0 && pix >= 4) ? 2 : 1;
@@ -268,8 +271,11 @@ extern "C" int hsb_patch_conv1x1_fwd(const void* x, const void* w, void* y,
     if (w_layout == HSB_W_PATCH_MAJOR)
         HSB_REQUIRE(w_row_stride >= p.hp, HSB_ERR_INVALID_ARG, "patch_conv1x1: w_row_stride < hyper params");
     p.ws = make_wstrides(w_layout, p.hp, (int64_t)fh * fw, w_row_stride);
-    p.wrow_smem = (p.hp + 7) / 8 * 8;
     const size_t es = dtype == HSB_F32 ? 4 : 2;
+    // staged weight rows start 16-byte aligned; an odd number of 16-byte units per row makes consecutive patches
+    // land in different bank groups (lanes of one warp read the same offset of different patches' rows)
+    p.wrow_smem = (p.hp + 7) / 8 * 8;
+    if (((size_t)p.wrow_smem * es / 16) % 2 == 0) p.wrow_smem += (int)(16 / es);
     p.bulk_ok = (w_layout == HSB_W_PATCH_MAJOR) && ((uintptr_t)w % 16 == 0) &&
                 ((size_t)p.hp * es) % 16 == 0 && ((size_t)w_row_stride * es) % 16 == 0;
     HSB_REQUIRE((int64_t)B * fh * fw < (1ll << 31), HSB_ERR_UNSUPPORTED, "patch_conv1x1: too many patches");

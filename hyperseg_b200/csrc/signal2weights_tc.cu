@@ -94,16 +94,27 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             if ((st ? stage_group1 : stage_group0) != g) {
                 unsigned char* a_dst = a_sm + st * a_bytes;
                 // unit(mc, k) = (k/8)*LBO + mc*128 + (k%8)*16: 8 consecutive positions of signal channel k
-                for (int i = lane; i < kpad * (HD_M / 8); i += 32) {
-                    const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
-                    const int n = n0 + mc * 8;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (k < p.spg && n < p.NTOT) {
-                        const int b = n / p.P, pp = n % p.P;          // P % 8 == 0: a unit never straddles images
-                        v = *reinterpret_cast<const uint4*>(p.s + (size_t)b * p.ssb +
-                                                            (size_t)(p.sig_index + g * p.spg + k) * p.ssc + pp);
+                const int units = kpad * (HD_M / 8);
+                for (int base = 0; base < units; base += 32 * 8) {      // 8 independent 16-byte loads in flight per lane
+                    uint4 v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int i = base + e * 32 + lane;
+                        const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
+                        const int n = n0 + mc * 8;
+                        v[e] = make_uint4(0, 0, 0, 0);
+                        if (i < units && k < p.spg && n < p.NTOT) {
+                            const int b = n / p.P, pp = n % p.P;          // P % 8 == 0: a unit never straddles images
+                            v[e] = __ldg(reinterpret_cast<const uint4*>(p.s + (size_t)b * p.ssb +
+                                                                        (size_t)(p.sig_index + g * p.spg + k) * p.ssc + pp));
+                        }
                     }
-                    *reinterpret_cast<uint4*>(a_dst + (k >> 3) * a_lbo + mc * 128 + (k & 7) * 16) = v;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int i = base + e * 32 + lane;
+                        const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
+                        if (i < units) *reinterpret_cast<uint4*>(a_dst + (k >> 3) * a_lbo + mc * 128 + (k & 7) * 16) = v[e];
+                    }
                 }
                 if (st) stage_group1 = g; else stage_group0 = g;
                 fence_proxy_async_smem();
