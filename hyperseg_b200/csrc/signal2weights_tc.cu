@@ -287,12 +287,13 @@ extern "C" int hsb_signal2weights_packed_fwd(const void* s, const void* packed, 
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("signal2weights_packed attr: ") + cudaGetErrorString(e));
     p.items = groups * p.otiles;
     const int tiles = ceil_div(p.NTOT, HD_M);
-    // split the items of a position tile over `splits` CTAs so that (waves of CTAs) x (items per CTA) is smallest;
-    // ties go to fewer, longer-running CTAs (the per-CTA set-up -- TMEM allocation, barriers -- is not free)
+    // split the items of a position tile over `splits` CTAs: minimise (waves of CTAs) x (items per CTA + set-up), where
+    // the per-CTA set-up (launch, TMEM allocation, barrier init, pipeline fill) is worth about four items (measured:
+    // one-item CTAs take ~10 us each)
     const int sms = std::max(1, device_sm_count());
-    int splits = 1, best = ceil_div(tiles, sms) * p.items;
+    int splits = 1, best = ceil_div(tiles, sms) * (p.items + 4);
     for (int sp = 2; sp <= p.items; ++sp) {
-        const int cost = ceil_div(tiles * sp, sms) * ceil_div(p.items, sp);
+        const int cost = ceil_div(tiles * sp, sms) * (ceil_div(p.items, sp) + 4);
         if (cost < best) { best = cost; splits = sp; }
     }
     p.splits = splits;
