@@ -123,7 +123,8 @@ template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
 patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic on the __shared__ array so the compiler keeps the address space (LDS/STS, not generic)
+    unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     __nv_bfloat16* rawX = reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_RAWX);

@@ -48,7 +48,8 @@ __host__ __device__ inline size_t head_smem_bytes(int kpad) {
 // warp / 4; TMEM -> bf16 -> staging rows -> coalesced stores, one item behind the MMAs.
 __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const HeadTCParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    // align by pointer arithmetic on the __shared__ array so the compiler keeps the address space (LDS/STS, not generic)
+    unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kpad = p.kpad;
     const size_t a_bytes = (size_t)kpad * HD_M * 2, b_bytes = (size_t)HD_NT * kpad * 2;
@@ -186,18 +187,31 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             if (nvalid > 0) {
                 const int ob = o_base + half * HC;
                 const bool pairs = (ob & 1) == 0;
-                for (int r = 0; r < 32; ++r) {
-                    const int n = n0 + q * 32 + r;
-                    if (n >= p.NTOT) break;
-                    const unsigned char* srow = st_sm + (size_t)(q * 32 + r) * HD_STAGE_PITCH + half * HC * 2;
-                    __nv_bfloat16* drow = p.out + (size_t)n * p.row_stride + ob;
-                    if (pairs) {
-                        for (int c = lane * 2; c < nvalid; c += 64) {
-                            if (c + 1 < nvalid) *reinterpret_cast<uint32_t*>(drow + c) = *reinterpret_cast<const uint32_t*>(srow + c * 2);
-                            else drow[c] = *reinterpret_cast<const __nv_bfloat16*>(srow + c * 2);
+                const int nrows = min(32, p.NTOT - (n0 + q * 32));
+                const unsigned char* sbase = st_sm + (size_t)(q * 32) * HD_STAGE_PITCH + half * HC * 2;
+                __nv_bfloat16* dbase = p.out + (size_t)(n0 + q * 32) * p.row_stride + ob;
+                if (pairs) {
+                    // lane = column pair, rows unrolled: 8 independent shared loads / global stores in flight;
+                    // for a fixed row the 32 lanes write 128 contiguous bytes
+                    for (int c = lane * 2; c < nvalid; c += 64) {
+                        const bool two = c + 1 < nvalid;
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r) {
+                            if (r < nrows) {
+                                const unsigned char* sp = sbase + (size_t)r * HD_STAGE_PITCH + c * 2;
+                                __nv_bfloat16* dp = dbase + (size_t)r * p.row_stride + c;
+                                if (two) *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
+                                else *dp = *reinterpret_cast<const __nv_bfloat16*>(sp);
+                            }
                         }
-                    } else {
-                        for (int c = lane; c < nvalid; c += 32) drow[c] = *reinterpret_cast<const __nv_bfloat16*>(srow + c * 2);
+                    }
+                } else {
+                    for (int c = lane; c < nvalid; c += 32) {
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r)
+                            if (r < nrows)
+                                dbase[(size_t)r * p.row_stride + c] =
+                                    *reinterpret_cast<const __nv_bfloat16*>(sbase + (size_t)r * HD_STAGE_PITCH + c * 2);
                     }
                 }
             }
