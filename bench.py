@@ -11,7 +11,8 @@ encoder + weight mapper, and the decoder running on libhsb200's CUDA kernels.
   value     whole-job frames/s with the frames already in HBM, device-timed (CUDA events), max over ranks
   e2e       the same through SegmentationEngine.__call__: pinned host frames -> H2D -> forward -> argmax -> D2H labels
   roofline  the dominant kernel (fused inverted-residual MetaBlock at decoder level 4) timed alone with CUDA events
-            on cold inputs: algorithmic bytes / time against the measured HBM peak (MEASURED_PEAKS.json);
+            around a graph of 12 launches on cold inputs (3 rotating buffer sets, 437 MB > L2): algorithmic bytes /
+            time against the measured HBM peak (MEASURED_PEAKS.json);
             `patch_conv` aggregates the five patch-wise kernels, `heads` the five weight heads
   cpu_baseline  the CPU port of the same forward (stock encoder + oracle decoder, fp32, all host threads) on a
             bounded sample (single frames); this is also what --impl reference times.
@@ -189,17 +190,33 @@ def kernel_rooflines(batch: int, iters: int = 12):
         return ((torch.rand(n, generator=g) + 0.5).to(dev), (torch.randn(n, generator=g) * 0.1).to(dev))
 
     def time_it(fn_sets):
-        for f in fn_sets:                       # warm-up (also sets func attributes / loads modules)
+        """Average device time of one launch.  The launches (rotating over the cold buffer sets) are captured in a
+        CUDA graph and replayed, so the CUDA events bracket device work only -- with eager launches the Python/ctypes
+        call path (tens of microseconds) would dominate kernels this short."""
+        for f in fn_sets:                       # warm-up (sets func attributes / loads modules / packs head weights)
             f()
         torch.cuda.synchronize()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-        for i in range(iters):
-            ev[i][0].record()
-            fn_sets[i % len(fn_sets)]()
-            ev[i][1].record()
+        side = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            for f in fn_sets:
+                f()
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(iters):
+                    fn_sets[i % len(fn_sets)]()
         torch.cuda.synchronize()
-        ts = sorted(a.elapsed_time(b) for a, b in ev)
-        return sum(ts) / len(ts), ts[len(ts) // 2]
+        times = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(side):
+                e0.record(side)
+                graph.replay()
+                e1.record(side)
+            side.synchronize()
+            times.append(e0.elapsed_time(e1) / iters)
+        times.sort()
+        return sum(times[1:-1]) / len(times[1:-1]), times[len(times) // 2]
 
     out = {}
     sets = 3
