@@ -1,25 +1,31 @@
-// Fused patch-wise inverted-residual MetaBlock -- bf16 tensor-core path (tcgen05 / TMEM / TMA), 16x16 patches.
+// Fused patch-wise inverted-residual MetaBlock -- bf16 tensor-core path (tcgen05 / TMEM / TMA), 16x16 and 8x8 patches.
 //
 // Same arithmetic as patch_ir.cu (reference hyperseg/models/hyperseg_v1_0.py:328-376), organised for sm_100a:
 //
-//   persistent CTAs (one per SM, 18 warps) walk the patches; for each patch
-//   P0  wait for the TMA engine: the (ph+2)x(pw+2) halo tile of x arrives through a 4-D tensor map (box
-//       32 x 18 x Cin starting 8 pixels left of the patch -- TMA wants 16-byte aligned rows --, zero fill outside the image) and the patch's weight row through cp.async.bulk;
-//       image-border patches get their reflect halo patched in shared memory;
-//   P1  re-stage: x tile -> UMMA operand A1 (MN-major, pixels contiguous, plus a constant-one channel that
-//       carries the BatchNorm shift), W1/W3 -> operands B1/B2 with the BatchNorm scale folded in and the
-//       shift as an extra K column, W2 -> packed bf16x2 taps.  The raw buffers are then free and the TMA
-//       loads of the NEXT patch are issued, so they overlap P2..P6;
-//   P2  GEMM1 on the tensor core: H[324 px x hid] = A1 . B1^T, three M=128 tiles accumulated in TMEM;
+//   persistent CTAs, TWO (16x16) or THREE (8x8) resident per SM so that one CTA's barrier / tensor-core / TMA
+//   latencies are covered by another CTA's arithmetic; each CTA walks its patches:
+//   P0  wait for the TMA engine: the (ph+2)x(pw+2) halo tile of x arrives through a 4-D tensor map (box starting 8
+//       pixels left of the patch -- TMA wants a 16-byte aligned innermost start --, zero fill outside the image) and
+//       the patch's weight row through cp.async.bulk; image-border patches get their reflect halo patched in place;
+//   P1  re-stage: x tile -> UMMA operand A1 (K-major, lanes over pixels: conflict-free, with a constant-one channel
+//       that carries the BatchNorm shift), W1/W3 -> operands B1/B2 with the BatchNorm scale folded in and the shift
+//       as an extra K column, W2 -> packed bf16x2 taps; then the next patch's weight row is prefetched;
+//   P2  GEMM1 on the tensor core: H[(ph+2)(pw+2) px x hid] = A1 . B1^T, M=128 tiles accumulated in TMEM;
 //   P3  epilogue 1: TMEM -> registers -> ReLU6 -> bf16 -> shared "hidden" tile [pixel][channel];
 //   P4  depthwise 3x3 + BN2 + ReLU6 on CUDA cores in packed bf16x2 (lane = channel pair, warp = tile column,
 //       3x3 register window sliding down the column), written straight into GEMM2's A operand
 //       (128B-swizzled K-major);
-//   P5  GEMM2: O[256 px x Cout] = A2 . B2^T (two M=128 tiles);
-//   P6  epilogue 2: TMEM -> registers -> bf16 -> NCHW global stores (32-byte row segments).
+//   P5  GEMM2: O[ph*pw px x Cout] = A2 . B2^T;
+//   P6  epilogue 2: TMEM -> registers -> bf16 -> NCHW global stores; the next patch's x tile is requested as soon as
+//       GEMM2 has released the buffer it lands in.
 //
-// The BatchNorm shifts ride inside the GEMMs (constant-one K column), so the epilogues are a clamp and a
-// convert.  Nothing but x, the weight row and y touches global memory.
+// Shared memory is time-shared inside a patch so that two patches-in-flight fit an SM (104 KB per CTA at the level-4
+// shape): region X holds A1+B1 during P1-P2 and the hidden tile during P3-P4; region Y holds the raw x tile during
+// P0-P1 and A2 during P4-P5.  Stale bytes left behind by the other tenant are finite bf16 values that only ever meet
+// zero weights (padding K columns) or land in accumulator rows nobody reads.  TMEM is time-shared the same way
+// (GEMM2's accumulators reuse GEMM1's columns).
+// The BatchNorm shifts ride inside the GEMMs (constant-one K column), so the epilogues are a clamp and a convert.
+// Nothing but x, the weight row and y touches global memory.
 #include <cuda.h>
 
 #include <mutex>
@@ -31,23 +37,22 @@ namespace hsb {
 
 constexpr int r16(int v) { return (v + 15) / 16 * 16; }
 constexpr int r8(int v) { return (v + 7) / 8 * 8; }
-
+constexpr int r128(int v) { return (v + 127) / 128 * 128; }
 constexpr int pow2_at_least(int v) { int p = 32; while (p < v) p *= 2; return p; }
 constexpr int imax(int a, int b) { return a > b ? a : b; }
+constexpr int imin(int a, int b) { return a < b ? a : b; }
 
 template <int CIN_, int HID_, int COUT_, int PS_>
 struct IRTC {
     static constexpr int CIN = CIN_, HID = HID_, COUT = COUT_;
     static constexpr int PH = PS_, PW = PS_, TH = PS_ + 2, TW = PS_ + 2;
-    // TMA needs a 16-byte aligned start in the innermost dimension: the box starts 8 pixels left of the patch
-    // (32 pixels wide), the halo tile's column 0 is box column XOFF.
+    // TMA needs a 16-byte aligned start in the innermost dimension: the box starts 8 pixels left of the patch,
+    // the halo tile's column 0 is box column XOFF.
     static constexpr int XOFF = 7, TWB = r8(XOFF + TW);
     static constexpr int T = TH * TW, O = PH * PW;
     static constexpr int K1 = r16(CIN + 1), N1 = r16(HID), K2 = r16(HID + 1), N2 = r16(COUT);
     static constexpr int M1T = (T + 127) / 128, M2T = (O + 127) / 128;
-    static constexpr int MC2 = M2T * 16;                   // m-chunks of A2
-    static constexpr int MC1 = M1T * 16;                   // m-chunks (8 pixels) of A1
-    static constexpr int G1 = (T + 7) / 8;                 // m-chunks that hold real pixels
+    static constexpr int MC1 = M1T * 16, MC2 = M2T * 16;   // 8-pixel chunks of the A operands
     static constexpr int HP = CIN * HID + 9 * HID + HID * COUT;
     static constexpr int R1 = CIN * HID, R2 = R1 + 9 * HID;
     static constexpr int NPAIR = HID / 2;
@@ -56,47 +61,44 @@ struct IRTC {
     static constexpr int HPITCH = r8(HID);                 // hidden tile pitch (elements), 16-byte multiple
     static constexpr int HPW = HPITCH / 2;                 // ... in 32-bit words
     static constexpr int KT2 = K2 > 64 ? K2 - 64 : 0;      // K extent of A2's non-swizzled tail
-    static constexpr int DW_WARPS = PW + (TAILP > 0 ? 1 : 0);
-    static constexpr int WARPS = imax(imax(4 * M1T, 4 * M2T), DW_WARPS);
+    static constexpr int DWW = 8;                          // warps that walk tile columns in the depthwise phase
+    static constexpr int WARPS = DWW + (TAILP > 0 ? 1 : 0);
     static constexpr int THREADS = 32 * WARPS;
-    static constexpr int D2COL = r16(M1T * N1);            // TMEM column of GEMM2's accumulators
-    static constexpr int TMEM_COLS = pow2_at_least(D2COL + M2T * N2);
+    static constexpr int TMEM_COLS = pow2_at_least(imax(M1T * N1, M2T * N2));   // GEMM2 reuses GEMM1's columns
     // UMMA operand strides (bytes)
     static constexpr int A1_SBO = 128, A1_LBO = MC1 * 128;
     static constexpr int B1_SBO = 128, B1_LBO = (N1 / 8) * 128;
     static constexpr int B2_SBO = 128, B2_LBO = (N2 / 8) * 128;
     static constexpr int A2T_SBO = 128, A2T_LBO = MC2 * 128;
     // shared memory map (bytes from a 1024-aligned base)
-    static constexpr int OFF_A2 = 0;
-    static constexpr int SZ_A2 = M2T * 128 * 128;
-    static constexpr int OFF_A2T = OFF_A2 + SZ_A2;
-    static constexpr int SZ_A2T = (KT2 / 8) * MC2 * 128;
-    static constexpr int OFF_A1 = OFF_A2T + SZ_A2T;
-    static constexpr int SZ_A1 = (K1 / 8) * MC1 * 128;
-    static constexpr int OFF_B1 = OFF_A1 + SZ_A1;
-    static constexpr int SZ_B1 = (K1 / 8) * (N1 / 8) * 128;
-    static constexpr int OFF_B2 = OFF_B1 + SZ_B1;
-    static constexpr int SZ_B2 = (K2 / 8) * (N2 / 8) * 128;
-    static constexpr int OFF_HID = OFF_B2 + SZ_B2;
-    static constexpr int SZ_HID = ((T * HPITCH * 2) + 127) / 128 * 128;
-    static constexpr int ZERO_BYTES = OFF_HID + SZ_HID;    // everything above is zero-initialised once
-    static constexpr int OFF_RAWX = ZERO_BYTES;
+    static constexpr int SZ_A2 = M2T * 128 * 128, SZ_A2T = (KT2 / 8) * MC2 * 128;
     static constexpr int SZ_RAWX = CIN * TH * TWB * 2;
-    static constexpr int OFF_RAWW = (OFF_RAWX + SZ_RAWX + 127) / 128 * 128;
-    static constexpr int SZ_RAWW = (HP * 2 + 15) / 16 * 16 + 16;
-    static constexpr int OFF_W2P = (OFF_RAWW + SZ_RAWW + 15) / 16 * 16;
+    static constexpr int SZ_A1 = (K1 / 8) * MC1 * 128, SZ_B1 = (K1 / 8) * (N1 / 8) * 128;
+    static constexpr int SZ_HID = r128(T * HPITCH * 2);
+    static constexpr int OFF_Y = 0;                                             // region Y: raw x tile | A2 (+ tail)
+    static constexpr int SZ_Y = r128(imax(SZ_RAWX, SZ_A2 + SZ_A2T));
+    static constexpr int OFF_RAWX = OFF_Y, OFF_A2 = OFF_Y, OFF_A2T = OFF_Y + SZ_A2;
+    static constexpr int OFF_X = OFF_Y + SZ_Y;                                  // region X: A1 + B1 | hidden tile
+    static constexpr int SZ_X = r128(imax(SZ_A1 + SZ_B1, SZ_HID));
+    static constexpr int OFF_A1 = OFF_X, OFF_B1 = OFF_X + SZ_A1, OFF_HID = OFF_X;
+    static constexpr int OFF_B2 = OFF_X + SZ_X;
+    static constexpr int SZ_B2 = (K2 / 8) * (N2 / 8) * 128;
+    static constexpr int OFF_RAWW = OFF_B2 + SZ_B2;
+    static constexpr int SZ_RAWW = r16(HP * 2) + 16;
+    static constexpr int OFF_W2P = r16(OFF_RAWW + SZ_RAWW);
     static constexpr int SZ_W2P = 10 * HPW * 4;
     static constexpr int OFF_BN = OFF_W2P + SZ_W2P;
     static constexpr int SZ_BN = (4 * HID + 2 * COUT) * 4;
-    static constexpr int OFF_BAR = (OFF_BN + SZ_BN + 15) / 16 * 16;
+    static constexpr int OFF_BAR = r16(OFF_BN + SZ_BN);
     static constexpr int OFF_COORD = OFF_BAR + 64;            // int[2][4]: (b, pi, pj) of the patch in flight
-    static constexpr int SMEM_BYTES = OFF_COORD + 32 + 1024;  // + slack for the 1024-byte alignment
-    // CTAs per SM: bounded by shared memory, TMEM columns and a 96-register budget per thread
-    static constexpr int CTAS = imax(1, (227 * 1024 / SMEM_BYTES) < (512 / TMEM_COLS) ? (227 * 1024 / SMEM_BYTES) : (512 / TMEM_COLS));
-    static constexpr int MINB = (CTAS * THREADS * 96 <= 65536) ? CTAS : imax(1, 65536 / (THREADS * 96));
+    static constexpr int USED_BYTES = OFF_COORD + 32;
+    static constexpr int SMEM_BYTES = USED_BYTES + 1024;      // + slack for the 1024-byte alignment
+    // CTAs per SM: bounded by shared memory, TMEM columns and the register file
+    static constexpr int CTAS = imax(1, imin(imin(227 * 1024 / SMEM_BYTES, 512 / TMEM_COLS), PS_ == 16 ? 2 : 3));
     static_assert(HID % 4 == 0 && HID <= 68, "hidden width must be a multiple of 4 and at most 68");
     static_assert(TAILP <= 2, "at most two channel pairs in the K tail");
-    static_assert(D2COL + M2T * N2 <= 512, "TMEM budget");
+    static_assert(PW % DWW == 0, "tile columns must divide among the depthwise warps");
+    static_assert(TMEM_COLS <= 512 && 1 + M1T + M2T <= 7, "TMEM / barrier budget");
     static_assert(PS_ == 8 || PS_ == 16, "patch size");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -119,8 +121,13 @@ __device__ __forceinline__ uint32_t pack_relu6(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
 template <class C>
-__global__ void __launch_bounds__(C::THREADS, C::MINB)
+__global__ void __launch_bounds__(C::THREADS, C::CTAS)
 patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p) {
     extern __shared__ unsigned char smem_dyn[];
     // align by pointer arithmetic on the __shared__ array so the compiler keeps the address space (LDS/STS, not generic)
@@ -143,7 +150,9 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     const uint32_t b2_addr = smem_u32(sm + C::OFF_B2);
 
     // ---------------- one-time setup ----------------
-    for (int i = tid; i < C::ZERO_BYTES / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    // every byte that the tensor core may read as padding must be a finite value: clear the whole arena once
+    for (int i = tid; i < C::OFF_BAR / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
     for (int i = tid; i < C::HID; i += C::THREADS) {
         s1[i] = p.bn[0][i]; b1[i] = p.bn[1][i]; s2[i] = p.bn[2][i]; b2[i] = p.bn[3][i];
     }
@@ -156,21 +165,6 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         tma_prefetch_desc(&xmap);
     }
     if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
-    __syncthreads();
-    // constant-one channels that carry the BatchNorm shifts through the GEMMs
-    {
-        const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
-        for (int m = tid; m < C::M2T * 128; m += C::THREADS) {    // A2: k = HID, every pixel row
-            if (C::HID < 64) {
-                int off = m * 128 + ((((C::HID / 8) ^ (m & 7)) * 16) + (C::HID % 8) * 2);
-                *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A2 + off) = one;
-            } else {
-                int k = C::HID - 64;
-                int off = (k / 8) * C::A2T_LBO + (m / 8) * C::A2T_SBO + (m & 7) * 16 + (k % 8) * 2;
-                *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A2T + off) = one;
-            }
-        }
-    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -178,18 +172,30 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
 
     const int P = p.fh * p.fw;
     constexpr uint32_t X_BYTES = C::SZ_RAWX;
-    constexpr uint32_t W_BYTES = (C::HP * 2 + 15) / 16 * 16;
-    auto issue_loads = [&](int patch, uint32_t slot) {         // one thread
+    constexpr uint32_t W_BYTES = r16(C::HP * 2);
+    // The loads of a patch are announced (expect_tx, coordinates) when its weight row is requested; the x tile is
+    // requested later, once its landing buffer (region Y) is free.  Both complete on bar_tma's current phase.
+    auto announce_and_load_w = [&](int patch, uint32_t slot) {         // one thread
         const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
         coord[slot * 4 + 0] = b; coord[slot * 4 + 1] = pi; coord[slot * 4 + 2] = pj;   // published by the arrive below
         mbar_arrive_expect_tx(bar_tma, X_BYTES + (p.w_bulk ? W_BYTES : 0));
-        tma_load_4d(rawX, &xmap, pj * C::PW - 8, pi * C::PH - 1, 0, b, bar_tma);
         if (p.w_bulk) bulk_g2s(rawW, p.w + (size_t)patch * p.w_row_stride, W_BYTES, bar_tma);
     };
-    if (tid == 0 && (int)blockIdx.x < p.total) issue_loads(blockIdx.x, 0);
+    auto load_x = [&](uint32_t slot) {                                 // one thread (the one that announced)
+        tma_load_4d(rawX, &xmap, coord[slot * 4 + 2] * C::PW - 8, coord[slot * 4 + 1] * C::PH - 1, 0, coord[slot * 4 + 0],
+                    bar_tma);
+    };
+    if (tid == 0 && (int)blockIdx.x < p.total) {
+        announce_and_load_w(blockIdx.x, 0);
+        load_x(0);
+    }
 
     constexpr uint32_t IDESC1 = idesc_bf16_f32(128, C::N1, false, false);
     constexpr uint32_t IDESC2 = idesc_bf16_f32(128, C::N2, false, false);
+    // TMEM lanes 32q..32q+31 are only reachable from warps with warp % 4 == q: a warp serves the (tile, quadrant)
+    // tasks of its own quadrant, tiles strided by the number of warps sharing that quadrant
+    const int q = warp & 3;
+    const int q_warps = (C::WARPS - q + 3) / 4, q_rank = warp >> 2;
 
     uint32_t it = 0;
     for (int patch = blockIdx.x; patch < p.total; patch += gridDim.x, ++it) {
@@ -213,8 +219,8 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         }
         if (top || bottom) {
             for (int i = tid; i < C::CIN * C::TW; i += C::THREADS) {
-                int c = i / C::TW, q = i % C::TW;
-                __nv_bfloat16* ch = rawX + (size_t)c * C::TH * C::TWB + C::XOFF + q;
+                int c = i / C::TW, qq = i % C::TW;
+                __nv_bfloat16* ch = rawX + (size_t)c * C::TH * C::TWB + C::XOFF + qq;
                 if (top) ch[0] = ch[2 * C::TWB];
                 if (bottom) ch[(C::TH - 1) * C::TWB] = ch[(C::TH - 3) * C::TWB];
             }
@@ -223,8 +229,9 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
 
         // ---------------- P1: re-stage into UMMA operand layouts ----------------
         {   // x tile -> A1 (K-major): unit(m, kc) = kc*LBO + (m/8)*SBO + (m%8)*16 bytes = 8 channels of pixel m.
-            // Lanes walk consecutive pixels: 2-byte reads of one tile row are contiguous, the 16-byte writes of a
-            // warp cover 512 contiguous bytes -> no bank conflicts either way.  Channel CIN is the constant one.
+            // Lanes walk consecutive pixels: 2-byte reads of one tile row are contiguous, the 16-byte writes of a warp
+            // cover 512 contiguous bytes -> no bank conflicts either way.  Channel CIN is the constant one; k-chunks
+            // past it keep whatever finite bytes the hidden tile left there (their B1 columns are zero).
             constexpr int KCX = (C::CIN + 1 + 7) / 8;
             constexpr int CHS = C::TH * C::TWB;                    // elements between channels of the raw tile
             for (int i = tid; i < KCX * C::T; i += C::THREADS) {
@@ -245,28 +252,29 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                 *reinterpret_cast<uint4*>(sm + C::OFF_A1 + kc * C::A1_LBO + (m >> 3) * C::A1_SBO + (m & 7) * 16) =
                     make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
             }
-            // W1 -> B1 (K-major): unit(n, kc) = kc*LBO + (n/8)*SBO + (n%8)*16; row n = s1[n]*W1[n][:], b1[n] at k=CIN
-            constexpr int KC1 = (C::CIN + 1 + 7) / 8;
-            for (int i = tid; i < C::HID * KC1; i += C::THREADS) {
-                const int n = i / KC1, kc = i % KC1;
-                const float sc = s1[n];
-                const __nv_bfloat16* src = rawW + n * C::CIN;
-                uint32_t v[4];
+            // W1 -> B1 (K-major): unit(n, kc) = kc*LBO + (n/8)*SBO + (n%8)*16; row n = s1[n]*W1[n][:], b1[n] at k=CIN.
+            // Every unit of B1 is rewritten (zeros for padding rows / columns): the region is shared with the hidden tile.
+            for (int i = tid; i < C::N1 * (C::K1 / 8); i += C::THREADS) {
+                const int n = i % C::N1, kc = i / C::N1;
+                uint32_t v[4] = {0u, 0u, 0u, 0u};
+                if (n < C::HID && kc * 8 <= C::CIN) {
+                    const float sc = s1[n];
+                    const __nv_bfloat16* src = rawW + n * C::CIN;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float f[2];
+                    for (int e = 0; e < 4; ++e) {
+                        float f[2];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int k = kc * 8 + e * 2 + h;
-                        f[h] = k < C::CIN ? __bfloat162float(src[k]) * sc : (k == C::CIN ? b1[n] : 0.f);
+                        for (int h = 0; h < 2; ++h) {
+                            const int k = kc * 8 + e * 2 + h;
+                            f[h] = k < C::CIN ? __bfloat162float(src[k]) * sc : (k == C::CIN ? b1[n] : 0.f);
+                        }
+                        v[e] = pack_bf16(f[0], f[1]);
                     }
-                    __nv_bfloat162 t = __floats2bfloat162_rn(f[0], f[1]);
-                    v[e] = *reinterpret_cast<uint32_t*>(&t);
                 }
                 *reinterpret_cast<uint4*>(sm + C::OFF_B1 + kc * C::B1_LBO + (n >> 3) * C::B1_SBO + (n & 7) * 16) =
                     make_uint4(v[0], v[1], v[2], v[3]);
             }
-            // W3 -> B2 (K-major): row n = s3[n]*W3[n][:], b3[n] at k=HID
+            // W3 -> B2 (K-major, own region: padding rows / columns stay zero from the set-up)
             constexpr int KC2 = (C::HID + 1 + 7) / 8;
             for (int i = tid; i < C::COUT * KC2; i += C::THREADS) {
                 const int n = i / KC2, kc = i % KC2;
@@ -281,8 +289,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                         const int k = kc * 8 + e * 2 + h;
                         f[h] = k < C::HID ? __bfloat162float(src[k]) * sc : (k == C::HID ? b3[n] : 0.f);
                     }
-                    __nv_bfloat162 t = __floats2bfloat162_rn(f[0], f[1]);
-                    v[e] = *reinterpret_cast<uint32_t*>(&t);
+                    v[e] = pack_bf16(f[0], f[1]);
                 }
                 *reinterpret_cast<uint4*>(sm + C::OFF_B2 + kc * C::B2_LBO + (n >> 3) * C::B2_SBO + (n & 7) * 16) =
                     make_uint4(v[0], v[1], v[2], v[3]);
@@ -297,15 +304,15 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                 } else {
                     lo = b2[2 * cp]; hi = b2[2 * cp + 1];
                 }
-                __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-                w2p[tap * C::HPW + cp] = *reinterpret_cast<uint32_t*>(&t);
+                w2p[tap * C::HPW + cp] = pack_bf16(lo, hi);
             }
         }
         fence_proxy_async_smem();          // operand writes -> visible to the tensor core (async proxy)
         tc_fence_before_sync();
         __syncthreads();
 
-        // ---------------- P2: GEMM1 + prefetch of the next patch ----------------
+        // ---------------- P2: GEMM1; the next patch's weight row starts to stream in ----------------
+        const int next = patch + gridDim.x;
         if (tid == 0) {
             tc_fence_after_sync();
             for (int t = 0; t < C::M1T; ++t) {
@@ -315,84 +322,74 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                     const uint64_t db = smem_desc(b1_addr + 2 * s * C::B1_LBO, C::B1_LBO, C::B1_SBO, SWZ_NONE);
                     umma_bf16(tmem + t * C::N1, da, db, IDESC1, s > 0);
                 }
-                umma_commit(bar_mma1 + t);          // epilogue of tile t can start while the next tile runs
+                umma_commit(bar_mma1 + t);
             }
-            const int next = patch + gridDim.x;
-            if (next < p.total) issue_loads(next, par ^ 1);     // raw buffers were fully consumed in P1
+            if (next < p.total) announce_and_load_w(next, par ^ 1);     // rawW was consumed in P1
         }
 
-        // ---------------- P3: epilogue 1 (TMEM -> ReLU6 -> hidden tile) ----------------
-        if (warp < 4 * C::M1T) {
-            const int t = warp >> 2, q = warp & 3;
+        // ---------------- P3: epilogue 1 (TMEM -> ReLU6 -> hidden tile, which overwrites A1/B1) ----------------
+        for (int t = 0; t < C::M1T; ++t) mbar_wait(bar_mma1 + t, par);      // every tile done: A1/B1 are dead
+        tc_fence_after_sync();
+        for (int t = q_rank; t < C::M1T; t += q_warps) {
+            if (t * 128 + q * 32 >= C::T) continue;             // warp-uniform: no real pixels in this quadrant
             const int m = t * 128 + q * 32 + lane;
-            if (t * 128 + q * 32 < C::T) {                     // warp-uniform: this quadrant holds real pixels
-                mbar_wait(bar_mma1 + t, par);
-                tc_fence_after_sync();
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + t * C::N1;
-                unsigned char* hrow = sm + C::OFF_HID + (size_t)m * (C::HPITCH * 2);
-                constexpr int FULL = C::HID / 16, REM = C::HID % 16;
-                static_assert(REM == 0 || REM == 4 || REM == 8 || REM == 12, "hidden width must be a multiple of 4");
-                // 32 columns per round trip: two loads in flight, one wait
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + t * C::N1;
+            unsigned char* hrow = sm + C::OFF_HID + (size_t)m * (C::HPITCH * 2);
+            constexpr int FULL = C::HID / 16, REM = C::HID % 16;
+            static_assert(REM == 0 || REM == 4 || REM == 8 || REM == 12, "hidden width must be a multiple of 4");
 #pragma unroll
-                for (int ch = 0; ch < FULL; ch += 2) {
-                    uint32_t v0[16], v1[16];
-                    tmem_ld16(taddr + ch * 16, v0);
-                    if (ch + 1 < FULL) tmem_ld16(taddr + (ch + 1) * 16, v1);
-                    tmem_ld_wait();
-                    uint32_t o[8];
+            for (int ch = 0; ch < FULL; ch += 2) {          // 32 columns per round trip: two loads in flight, one wait
+                uint32_t v0[16], v1[16];
+                tmem_ld16(taddr + ch * 16, v0);
+                if (ch + 1 < FULL) tmem_ld16(taddr + (ch + 1) * 16, v1);
+                tmem_ld_wait();
+                uint32_t o[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = pack_relu6(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1]));
+                for (int e = 0; e < 8; ++e) o[e] = pack_relu6(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1]));
+                if (m < C::T) {
+                    *reinterpret_cast<uint4*>(hrow + ch * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<uint4*>(hrow + ch * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+                if (ch + 1 < FULL) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = pack_relu6(__uint_as_float(v1[2 * e]), __uint_as_float(v1[2 * e + 1]));
                     if (m < C::T) {
-                        *reinterpret_cast<uint4*>(hrow + ch * 32) = make_uint4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<uint4*>(hrow + ch * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
-                    }
-                    if (ch + 1 < FULL) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = pack_relu6(__uint_as_float(v1[2 * e]), __uint_as_float(v1[2 * e + 1]));
-                        if (m < C::T) {
-                            *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32) = make_uint4(o[0], o[1], o[2], o[3]);
-                            *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
-                        }
+                        *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
                     }
                 }
-                if (REM > 0) {
-                    uint32_t v8[8], v4[4];
-                    if (REM >= 8) tmem_ld8(taddr + FULL * 16, v8);
-                    constexpr int c4 = FULL * 16 + (REM >= 8 ? 8 : 0);
-                    if (REM % 8 == 4) tmem_ld4(taddr + c4, v4);
-                    tmem_ld_wait();
-                    if (REM >= 8) {
-                        uint32_t o[4];
+            }
+            if (REM > 0) {
+                uint32_t v8[8], v4[4];
+                if (REM >= 8) tmem_ld8(taddr + FULL * 16, v8);
+                constexpr int c4 = FULL * 16 + (REM >= 8 ? 8 : 0);
+                if (REM % 8 == 4) tmem_ld4(taddr + c4, v4);
+                tmem_ld_wait();
+                if (REM >= 8) {
+                    uint32_t o[4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) o[e] = pack_relu6(__uint_as_float(v8[2 * e]), __uint_as_float(v8[2 * e + 1]));
-                        if (m < C::T) *reinterpret_cast<uint4*>(hrow + FULL * 32) = make_uint4(o[0], o[1], o[2], o[3]);
-                    }
-                    if (REM % 8 == 4) {
-                        uint32_t o0 = pack_relu6(__uint_as_float(v4[0]), __uint_as_float(v4[1]));
-                        uint32_t o1 = pack_relu6(__uint_as_float(v4[2]), __uint_as_float(v4[3]));
-                        if (m < C::T) *reinterpret_cast<uint2*>(hrow + c4 * 2) = make_uint2(o0, o1);
-                    }
+                    for (int e = 0; e < 4; ++e) o[e] = pack_relu6(__uint_as_float(v8[2 * e]), __uint_as_float(v8[2 * e + 1]));
+                    if (m < C::T) *reinterpret_cast<uint4*>(hrow + FULL * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                if (REM % 8 == 4) {
+                    uint32_t o0 = pack_relu6(__uint_as_float(v4[0]), __uint_as_float(v4[1]));
+                    uint32_t o1 = pack_relu6(__uint_as_float(v4[2]), __uint_as_float(v4[3]));
+                    if (m < C::T) *reinterpret_cast<uint2*>(hrow + c4 * 2) = make_uint2(o0, o1);
                 }
             }
         }
         tc_fence_before_sync();
         __syncthreads();
 
-        // ---------------- P4: depthwise 3x3 + BN2 + ReLU6 -> A2 ----------------
+        // ---------------- P4: depthwise 3x3 + BN2 + ReLU6 -> A2 (which overwrites the raw x tile) ----------------
         {
             const uint32_t* hid = reinterpret_cast<const uint32_t*>(sm + C::OFF_HID);
-            int cp = -1, v = 0;
-            bool tail = false;
-            if (warp < C::PW) { if (lane < C::MAINP) { cp = lane; v = warp; } }
-            else if (warp == C::PW && C::TAILP > 0) {
-                if ((lane % 2) < C::TAILP && (lane >> 1) < C::PW) { cp = 32 + (lane & 1); v = lane >> 1; tail = true; }
-            }
-            if (cp >= 0) {
+            const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f), six = __floats2bfloat162_rn(6.f, 6.f);
+            auto column = [&](int cp, int v, unsigned char* dst, int dst_step) {
                 __nv_bfloat162 wt[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) wt[k] = *reinterpret_cast<const __nv_bfloat162*>(&w2p[k * C::HPW + cp]);
                 const __nv_bfloat162 bias = *reinterpret_cast<const __nv_bfloat162*>(&w2p[9 * C::HPW + cp]);
-                const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f), six = __floats2bfloat162_rn(6.f, 6.f);
                 const uint32_t* col = hid + v * C::HPW + cp;               // pixel (r, v + kx) at (r*TW + v + kx)*HPW
                 __nv_bfloat162 r0[3], r1[3], r2[3];
 #pragma unroll
@@ -408,21 +405,48 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                         uint32_t a = col[((u + 2) * C::TW + kx) * C::HPW];
                         r2[kx] = *reinterpret_cast<__nv_bfloat162*>(&a);
                     }
-                    __nv_bfloat162 acc = bias;
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        acc = __hfma2(wt[kx], r0[kx], acc);
-                        acc = __hfma2(wt[3 + kx], r1[kx], acc);
-                        acc = __hfma2(wt[6 + kx], r2[kx], acc);
-                    }
+                    // three independent partial sums (one per kernel row) keep the FMA chain short
+                    __nv_bfloat162 a0 = __hfma2(wt[0], r0[0], bias), a1 = __hmul2(wt[3], r1[0]), a2 = __hmul2(wt[6], r2[0]);
+                    a0 = __hfma2(wt[1], r0[1], a0); a1 = __hfma2(wt[4], r1[1], a1); a2 = __hfma2(wt[7], r2[1], a2);
+                    a0 = __hfma2(wt[2], r0[2], a0); a1 = __hfma2(wt[5], r1[2], a1); a2 = __hfma2(wt[8], r2[2], a2);
+                    __nv_bfloat162 acc = __hadd2(__hadd2(a0, a1), a2);
                     acc = __hmin2(__hmax2(acc, zero), six);
-                    const int m = u * C::PW + v;
-                    uint32_t off;
-                    if (!tail) off = C::OFF_A2 + m * 128 + ((((cp >> 2) ^ (m & 7)) << 4) | ((cp & 3) << 2));
-                    else off = C::OFF_A2T + (m >> 3) * C::A2T_SBO + (m & 7) * 16 + (cp - 32) * 4;
-                    *reinterpret_cast<uint32_t*>(sm + off) = *reinterpret_cast<uint32_t*>(&acc);
+                    *reinterpret_cast<uint32_t*>(dst + u * dst_step) = *reinterpret_cast<uint32_t*>(&acc);
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) { r0[kx] = r1[kx]; r1[kx] = r2[kx]; }
+                }
+            };
+            if (warp < C::DWW) {
+                if (lane < C::MAINP) {
+                    const int cp = lane;
+#pragma unroll 1
+                    for (int v = warp; v < C::PW; v += C::DWW) {
+                        // pixel m = u*PW + v: 128-byte swizzled row m, 16-byte chunk (cp/4) ^ (m%8); m%8 == v%8 for all u
+                        unsigned char* dst = sm + C::OFF_A2 + v * 128 + ((((cp >> 2) ^ (v & 7)) << 4) | ((cp & 3) << 2));
+                        column(cp, v, dst, C::PW * 128);
+                    }
+                }
+            } else if (C::TAILP > 0) {
+                // tail warp: channel pairs 32.. (K >= 64, non-swizzled units) for every column, then the constant-one column
+                const int v = lane >> 1;
+                if ((lane & 1) < C::TAILP && v < C::PW) {
+                    const int cp = 32 + (lane & 1);
+                    unsigned char* dst = sm + C::OFF_A2T + (v >> 3) * C::A2T_SBO + (v & 7) * 16 + (cp - 32) * 4;
+                    column(cp, v, dst, (C::PW / 8) * C::A2T_SBO);
+                }
+            }
+            // K columns HID..K2-1 of A2: the constant one that carries BN3's shift, then zeros.  Rewritten every patch
+            // because region Y also hosts the raw x tile (whose bytes must never meet the tensor core as padding).
+            const int ones_warp = C::TAILP > 0 ? C::DWW : 0;
+            if (warp == ones_warp) {
+                constexpr int NPADW = (C::K2 - C::HID) / 2;                 // 32-bit words per row (HID and K2 are even)
+                for (int i = lane; i < C::M2T * 128 * NPADW; i += 32) {
+                    const int m = i / NPADW, k = C::HID + (i % NPADW) * 2;
+                    const uint32_t val = (k == C::HID) ? 0x00003F80u : 0u;  // (bf16 1.0, bf16 0.0)
+                    unsigned char* dst;
+                    if (k < 64) dst = sm + C::OFF_A2 + m * 128 + ((((k >> 3) ^ (m & 7)) << 4) | ((k & 7) << 1));
+                    else dst = sm + C::OFF_A2T + ((k - 64) >> 3) * C::A2T_LBO + (m >> 3) * C::A2T_SBO + (m & 7) * 16 + ((k - 64) & 7) * 2;
+                    *reinterpret_cast<uint32_t*>(dst) = val;
                 }
             }
         }
@@ -430,29 +454,33 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         tc_fence_before_sync();
         __syncthreads();
 
-        // ---------------- P5: GEMM2 ----------------
+        // ---------------- P5: GEMM2 (accumulators reuse GEMM1's TMEM columns) ----------------
         if (tid == 0) {
             tc_fence_after_sync();
             for (int t = 0; t < C::M2T; ++t) {
 #pragma unroll
                 for (int s = 0; s < C::K2 / 16; ++s) {
                     uint64_t da;
-                    if (s < 4) da = smem_desc(a2_addr + t * 128 * 128 + s * 32, 16, 1024, SWZ_128B);   // K2 <= 64 or s < 4
+                    if (s < 4) da = smem_desc(a2_addr + t * 128 * 128 + s * 32, 16, 1024, SWZ_128B);
                     else da = smem_desc(a2t_addr + 2 * (s - 4) * C::A2T_LBO + t * 16 * C::A2T_SBO, C::A2T_LBO, C::A2T_SBO, SWZ_NONE);
                     const uint64_t db = smem_desc(b2_addr + 2 * s * C::B2_LBO, C::B2_LBO, C::B2_SBO, SWZ_NONE);
-                    umma_bf16(tmem + C::D2COL + t * C::N2, da, db, IDESC2, s > 0);
+                    umma_bf16(tmem + t * C::N2, da, db, IDESC2, s > 0);
                 }
                 umma_commit(bar_mma2 + t);
+            }
+            // region Y is free once GEMM2 has read A2: request the next patch's x tile
+            if (next < p.total) {
+                for (int t = 0; t < C::M2T; ++t) mbar_wait(bar_mma2 + t, par);
+                load_x(par ^ 1);
             }
         }
 
         // ---------------- P6: epilogue 2 (TMEM -> bf16 -> NCHW) ----------------
-        if (warp < 4 * C::M2T) {
-            const int t = warp >> 2, q = warp & 3;
+        for (int t = q_rank; t < C::M2T; t += q_warps) {
             mbar_wait(bar_mma2 + t, par);
             tc_fence_after_sync();
             const int m = t * 128 + q * 32 + lane;
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + C::D2COL + t * C::N2;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + t * C::N2;
             const int u = m / C::PW, vv = m % C::PW;
             __nv_bfloat16* yp = p.y + (((size_t)b * C::COUT) * p.H + (size_t)pi * C::PH + u) * p.W + (size_t)pj * C::PW + vv;
             const size_t plane = (size_t)p.H * p.W;
@@ -511,7 +539,7 @@ static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
     auto kern = patch_ir_tc_kernel<C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("patch_ir_tc attr: ") + cudaGetErrorString(e));
-    const int grid = std::min(p.total, std::max(1, device_sm_count()) * C::MINB);
+    const int grid = std::min(p.total, std::max(1, device_sm_count()) * C::CTAS);
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
     return check_launch("patch_ir_tc launch");
 }
