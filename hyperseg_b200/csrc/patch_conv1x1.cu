@@ -202,11 +202,13 @@ static int launch_1x1(const Conv1x1Params& p, size_t smem, cudaStream_t st) {
         auto k = patch_conv1x1_kernel<T, OB, PB, true>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("conv1x1 attr: ") + cudaGetErrorString(e));
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         k<<<grid, 128, smem, st>>>(p);
     } else {
         auto k = patch_conv1x1_kernel<T, OB, PB, false>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("conv1x1 attr: ") + cudaGetErrorString(e));
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         k<<<grid, 128, smem, st>>>(p);
     }
     return check_launch("patch_conv1x1 launch");

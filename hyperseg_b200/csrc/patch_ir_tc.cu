@@ -28,6 +28,7 @@
 // Nothing but x, the weight row and y touches global memory.
 #include <cuda.h>
 
+#include <cstdio>
 #include <mutex>
 
 #include "common.cuh"
@@ -539,7 +540,17 @@ static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
     auto kern = patch_ir_tc_kernel<C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("patch_ir_tc attr: ") + cudaGetErrorString(e));
-    const int grid = std::min(p.total, std::max(1, device_sm_count()) * C::CTAS);
+    // ask for the largest shared-memory carve-out, otherwise the driver may size it for a single CTA
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int resident = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, C::THREADS, C::SMEM_BYTES) != cudaSuccess || resident < 1) {
+        cudaGetLastError();
+        resident = 1;
+    }
+    static const bool verbose = [] { const char* v = getenv("HSB_VERBOSE"); return v && v[0] == '1'; }();
+    if (verbose) fprintf(stderr, "[hsb] patch_ir_tc<%d,%d,%d,%d>: %d threads, %d B smem, %d CTAs/SM resident (design %d)\n",
+                         C::CIN, C::HID, C::COUT, C::PH, C::THREADS, C::SMEM_BYTES, resident, C::CTAS);
+    const int grid = std::min(p.total, std::max(1, device_sm_count()) * std::min(resident, C::CTAS));
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
     return check_launch("patch_ir_tc launch");
 }

@@ -1,5 +1,6 @@
 """Launch one decoder kernel a few times at its HyperSeg-M batch-8 shape (for ncu captures)."""
 import os, sys
+os.environ.setdefault("HSB_VERBOSE", "1")
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hyperseg_b200 import ops
