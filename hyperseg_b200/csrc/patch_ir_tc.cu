@@ -542,15 +542,17 @@ static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("patch_ir_tc attr: ") + cudaGetErrorString(e));
     // ask for the largest shared-memory carve-out, otherwise the driver may size it for a single CTA
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    int resident = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, C::THREADS, C::SMEM_BYTES) != cudaSuccess || resident < 1) {
-        cudaGetLastError();
-        resident = 1;
-    }
+    static const int force_ctas = [] { const char* v = getenv("HSB_IR_CTAS"); return v ? atoi(v) : 0; }();
+    const int ctas = force_ctas > 0 ? force_ctas : C::CTAS;
     static const bool verbose = [] { const char* v = getenv("HSB_VERBOSE"); return v && v[0] == '1'; }();
-    if (verbose) fprintf(stderr, "[hsb] patch_ir_tc<%d,%d,%d,%d>: %d threads, %d B smem, %d CTAs/SM resident (design %d)\n",
-                         C::CIN, C::HID, C::COUT, C::PH, C::THREADS, C::SMEM_BYTES, resident, C::CTAS);
-    const int grid = std::min(p.total, std::max(1, device_sm_count()) * std::min(resident, C::CTAS));
+    if (verbose) {
+        int resident = -1;
+        cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, C::THREADS, (size_t)C::SMEM_BYTES);
+        fprintf(stderr, "[hsb] patch_ir_tc<%d,%d,%d,%d>: %d threads, %d B smem, occupancy query -> %d (%s), launching %d CTAs/SM\n",
+                C::CIN, C::HID, C::COUT, C::PH, C::THREADS, C::SMEM_BYTES, resident, cudaGetErrorString(oe), ctas);
+        cudaGetLastError();
+    }
+    const int grid = std::min(p.total, std::max(1, device_sm_count()) * ctas);
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
     return check_launch("patch_ir_tc launch");
 }

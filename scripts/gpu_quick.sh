@@ -1,6 +1,3 @@
 #!/bin/bash
-mkdir -p gpurun_out
-HSB_VERBOSE=1 timeout 120 python scripts/run_kernel.py ir 2>&1 | tail -3
-HSB_VERBOSE=1 timeout 120 python scripts/run_kernel.py ir3 2>&1 | tail -3
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.log 2>&1
-echo "bench exit: $?"
+for c in 1 2 3; do HSB_VERBOSE=1 HSB_IR_CTAS=$c timeout 120 python scripts/time_kernel.py ir 2>&1 | tail -2; done
+for c in 1 2 3 4; do HSB_IR_CTAS=$c timeout 120 python scripts/time_kernel.py ir3 2>&1 | tail -1; done
