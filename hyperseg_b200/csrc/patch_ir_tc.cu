@@ -16,12 +16,11 @@
 //       3x3 register window sliding down the column), written straight into GEMM2's A operand
 //       (128B-swizzled K-major);
 //   P5  GEMM2: O[ph*pw px x Cout] = A2 . B2^T;
-//   P6  epilogue 2: TMEM -> registers -> bf16 -> NCHW global stores; the next patch's x tile is requested as soon as
-//       GEMM2 has released the buffer it lands in.
+//   P6  epilogue 2: TMEM -> registers -> bf16 -> NCHW global stores (the next x tile has been in flight since P5).
 //
-// Shared memory is time-shared inside a patch so that two patches-in-flight fit an SM (104 KB per CTA at the level-4
-// shape): region X holds A1+B1 during P1-P2 and the hidden tile during P3-P4; region Y holds the raw x tile during
-// P0-P1 and A2 during P4-P5.  Stale bytes left behind by the other tenant are finite bf16 values that only ever meet
+// Shared memory is time-shared inside a patch so that two patches-in-flight fit an SM (~110 KB per CTA at the level-4
+// shape): region Y holds A1+B1 during P1-P2 and A2 during P4-P5; region X holds the raw x tile during P0-P1 and the
+// hidden tile during P3-P4, so the next x tile can be requested as soon as the depthwise phase has consumed the hidden tile.  Stale bytes left behind by the other tenant are finite bf16 values that only ever meet
 // zero weights (padding K columns) or land in accumulator rows nobody reads.  TMEM is time-shared the same way
 // (GEMM2's accumulators reuse GEMM1's columns).
 // The BatchNorm shifts ride inside the GEMMs (constant-one K column), so the epilogues are a clamp and a convert.
@@ -76,12 +75,12 @@ struct IRTC {
     static constexpr int SZ_RAWX = CIN * TH * TWB * 2;
     static constexpr int SZ_A1 = (K1 / 8) * MC1 * 128, SZ_B1 = (K1 / 8) * (N1 / 8) * 128;
     static constexpr int SZ_HID = r128(T * HPITCH * 2);
-    static constexpr int OFF_Y = 0;                                             // region Y: raw x tile | A2 (+ tail)
-    static constexpr int SZ_Y = r128(imax(SZ_RAWX, SZ_A2 + SZ_A2T));
-    static constexpr int OFF_RAWX = OFF_Y, OFF_A2 = OFF_Y, OFF_A2T = OFF_Y + SZ_A2;
-    static constexpr int OFF_X = OFF_Y + SZ_Y;                                  // region X: A1 + B1 | hidden tile
-    static constexpr int SZ_X = r128(imax(SZ_A1 + SZ_B1, SZ_HID));
-    static constexpr int OFF_A1 = OFF_X, OFF_B1 = OFF_X + SZ_A1, OFF_HID = OFF_X;
+    static constexpr int OFF_Y = 0;                                             // region Y: A1 + B1 (P1-P2) | A2 (+ tail) (P4-P5)
+    static constexpr int SZ_Y = r128(imax(SZ_A1 + SZ_B1, SZ_A2 + SZ_A2T));
+    static constexpr int OFF_A2 = OFF_Y, OFF_A2T = OFF_Y + SZ_A2, OFF_A1 = OFF_Y, OFF_B1 = OFF_Y + SZ_A1;
+    static constexpr int OFF_X = OFF_Y + SZ_Y;                                  // region X: raw x tile (P0-P1) | hidden tile (P3-P4)
+    static constexpr int SZ_X = r128(imax(SZ_RAWX, SZ_HID));
+    static constexpr int OFF_RAWX = OFF_X, OFF_HID = OFF_X;
     static constexpr int OFF_B2 = OFF_X + SZ_X;
     static constexpr int SZ_B2 = (K2 / 8) * (N2 / 8) * 128;
     static constexpr int OFF_RAWW = OFF_B2 + SZ_B2;
@@ -232,7 +231,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         {   // x tile -> A1 (K-major): unit(m, kc) = kc*LBO + (m/8)*SBO + (m%8)*16 bytes = 8 channels of pixel m.
             // Lanes walk consecutive pixels: 2-byte reads of one tile row are contiguous, the 16-byte writes of a warp
             // cover 512 contiguous bytes -> no bank conflicts either way.  Channel CIN is the constant one; k-chunks
-            // past it keep whatever finite bytes the hidden tile left there (their B1 columns are zero).
+            // past it keep whatever finite bytes A2 left there (their B1 columns are zero).
             constexpr int KCX = (C::CIN + 1 + 7) / 8;
             constexpr int CHS = C::TH * C::TWB;                    // elements between channels of the raw tile
             for (int i = tid; i < KCX * C::T; i += C::THREADS) {
@@ -254,7 +253,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                     make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
             }
             // W1 -> B1 (K-major): unit(n, kc) = kc*LBO + (n/8)*SBO + (n%8)*16; row n = s1[n]*W1[n][:], b1[n] at k=CIN.
-            // Every unit of B1 is rewritten (zeros for padding rows / columns): the region is shared with the hidden tile.
+            // Every unit of B1 is rewritten (zeros for padding rows / columns): the region is shared with A2.
             for (int i = tid; i < C::N1 * (C::K1 / 8); i += C::THREADS) {
                 const int n = i % C::N1, kc = i / C::N1;
                 uint32_t v[4] = {0u, 0u, 0u, 0u};
@@ -328,8 +327,8 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
             if (next < p.total) announce_and_load_w(next, par ^ 1);     // rawW was consumed in P1
         }
 
-        // ---------------- P3: epilogue 1 (TMEM -> ReLU6 -> hidden tile, which overwrites A1/B1) ----------------
-        for (int t = 0; t < C::M1T; ++t) mbar_wait(bar_mma1 + t, par);      // every tile done: A1/B1 are dead
+        // ---------------- P3: epilogue 1 (TMEM -> ReLU6 -> hidden tile, which overwrites the raw x tile) ----------------
+        for (int t = 0; t < C::M1T; ++t) mbar_wait(bar_mma1 + t, par);      // every tile done: A1/B1 are dead (P4 overwrites them)
         tc_fence_after_sync();
         for (int t = q_rank; t < C::M1T; t += q_warps) {
             if (t * 128 + q * 32 >= C::T) continue;             // warp-uniform: no real pixels in this quadrant
@@ -382,7 +381,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         tc_fence_before_sync();
         __syncthreads();
 
-        // ---------------- P4: depthwise 3x3 + BN2 + ReLU6 -> A2 (which overwrites the raw x tile) ----------------
+        // ---------------- P4: depthwise 3x3 + BN2 + ReLU6 -> A2 (which overwrites A1/B1) ----------------
         {
             const uint32_t* hid = reinterpret_cast<const uint32_t*>(sm + C::OFF_HID);
             const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f), six = __floats2bfloat162_rn(6.f, 6.f);
@@ -417,14 +416,53 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                     for (int kx = 0; kx < 3; ++kx) { r0[kx] = r1[kx]; r1[kx] = r2[kx]; }
                 }
             };
+            // two columns per thread, walked in lockstep: twice the independent work per warp
+            auto column_pair = [&](int cp, int va, int vb, unsigned char* dsta, unsigned char* dstb, int dst_step) {
+                __nv_bfloat162 wt[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) wt[k] = *reinterpret_cast<const __nv_bfloat162*>(&w2p[k * C::HPW + cp]);
+                const __nv_bfloat162 bias = *reinterpret_cast<const __nv_bfloat162*>(&w2p[9 * C::HPW + cp]);
+                const uint32_t* cola = hid + va * C::HPW + cp;
+                const uint32_t* colb = hid + vb * C::HPW + cp;
+                __nv_bfloat162 a0r[3], a1r[3], a2r[3], b0r[3], b1r[3], b2r[3];
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    uint32_t t0 = cola[(0 * C::TW + kx) * C::HPW], t1 = cola[(1 * C::TW + kx) * C::HPW];
+                    uint32_t t2 = colb[(0 * C::TW + kx) * C::HPW], t3 = colb[(1 * C::TW + kx) * C::HPW];
+                    a0r[kx] = *reinterpret_cast<__nv_bfloat162*>(&t0); a1r[kx] = *reinterpret_cast<__nv_bfloat162*>(&t1);
+                    b0r[kx] = *reinterpret_cast<__nv_bfloat162*>(&t2); b1r[kx] = *reinterpret_cast<__nv_bfloat162*>(&t3);
+                }
+#pragma unroll
+                for (int u = 0; u < C::PH; ++u) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        uint32_t t0 = cola[((u + 2) * C::TW + kx) * C::HPW], t1 = colb[((u + 2) * C::TW + kx) * C::HPW];
+                        a2r[kx] = *reinterpret_cast<__nv_bfloat162*>(&t0); b2r[kx] = *reinterpret_cast<__nv_bfloat162*>(&t1);
+                    }
+                    __nv_bfloat162 pa0 = __hfma2(wt[0], a0r[0], bias), pa1 = __hmul2(wt[3], a1r[0]), pa2 = __hmul2(wt[6], a2r[0]);
+                    __nv_bfloat162 pb0 = __hfma2(wt[0], b0r[0], bias), pb1 = __hmul2(wt[3], b1r[0]), pb2 = __hmul2(wt[6], b2r[0]);
+                    pa0 = __hfma2(wt[1], a0r[1], pa0); pa1 = __hfma2(wt[4], a1r[1], pa1); pa2 = __hfma2(wt[7], a2r[1], pa2);
+                    pb0 = __hfma2(wt[1], b0r[1], pb0); pb1 = __hfma2(wt[4], b1r[1], pb1); pb2 = __hfma2(wt[7], b2r[1], pb2);
+                    pa0 = __hfma2(wt[2], a0r[2], pa0); pa1 = __hfma2(wt[5], a1r[2], pa1); pa2 = __hfma2(wt[8], a2r[2], pa2);
+                    pb0 = __hfma2(wt[2], b0r[2], pb0); pb1 = __hfma2(wt[5], b1r[2], pb1); pb2 = __hfma2(wt[8], b2r[2], pb2);
+                    __nv_bfloat162 ra = __hmin2(__hmax2(__hadd2(__hadd2(pa0, pa1), pa2), zero), six);
+                    __nv_bfloat162 rb = __hmin2(__hmax2(__hadd2(__hadd2(pb0, pb1), pb2), zero), six);
+                    *reinterpret_cast<uint32_t*>(dsta + u * dst_step) = *reinterpret_cast<uint32_t*>(&ra);
+                    *reinterpret_cast<uint32_t*>(dstb + u * dst_step) = *reinterpret_cast<uint32_t*>(&rb);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) { a0r[kx] = a1r[kx]; a1r[kx] = a2r[kx]; b0r[kx] = b1r[kx]; b1r[kx] = b2r[kx]; }
+                }
+            };
             if (warp < C::DWW) {
                 if (lane < C::MAINP) {
                     const int cp = lane;
+                    // pixel m = u*PW + v: 128-byte swizzled row m, 16-byte chunk (cp/4) ^ (m%8); m%8 == v%8 for all u
+                    auto a2_dst = [&](int v) { return sm + C::OFF_A2 + v * 128 + ((((cp >> 2) ^ (v & 7)) << 4) | ((cp & 3) << 2)); };
+                    if (C::PW == 2 * C::DWW) {
+                        column_pair(cp, warp, warp + C::DWW, a2_dst(warp), a2_dst(warp + C::DWW), C::PW * 128);
+                    } else {
 #pragma unroll 1
-                    for (int v = warp; v < C::PW; v += C::DWW) {
-                        // pixel m = u*PW + v: 128-byte swizzled row m, 16-byte chunk (cp/4) ^ (m%8); m%8 == v%8 for all u
-                        unsigned char* dst = sm + C::OFF_A2 + v * 128 + ((((cp >> 2) ^ (v & 7)) << 4) | ((cp & 3) << 2));
-                        column(cp, v, dst, C::PW * 128);
+                        for (int v = warp; v < C::PW; v += C::DWW) column(cp, v, a2_dst(v), C::PW * 128);
                     }
                 }
             } else if (C::TAILP > 0) {
@@ -436,18 +474,22 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                     column(cp, v, dst, (C::PW / 8) * C::A2T_SBO);
                 }
             }
-            // K columns HID..K2-1 of A2: the constant one that carries BN3's shift, then zeros.  Rewritten every patch
-            // because region Y also hosts the raw x tile (whose bytes must never meet the tensor core as padding).
-            const int ones_warp = C::TAILP > 0 ? C::DWW : 0;
-            if (warp == ones_warp) {
-                constexpr int NPADW = (C::K2 - C::HID) / 2;                 // 32-bit words per row (HID and K2 are even)
-                for (int i = lane; i < C::M2T * 128 * NPADW; i += 32) {
-                    const int m = i / NPADW, k = C::HID + (i % NPADW) * 2;
-                    const uint32_t val = (k == C::HID) ? 0x00003F80u : 0u;  // (bf16 1.0, bf16 0.0)
+            // K columns HID..K2-1 of A2: the constant one that carries BN3's shift, then zeros, written as whole / half
+            // 16-byte units.  Rewritten every patch because region Y also hosts A1/B1 (whose bytes must never meet the
+            // tensor core as padding).  HID is a multiple of 4, so the first unit is either whole or its upper half.
+            {
+                constexpr int U0 = C::HID / 8, U1 = C::K2 / 8;              // 16-byte units [U0, U1) contain padding
+                for (int i = tid; i < C::M2T * 128 * (U1 - U0); i += C::THREADS) {
+                    const int m = i / (U1 - U0), u = U0 + i % (U1 - U0);
                     unsigned char* dst;
-                    if (k < 64) dst = sm + C::OFF_A2 + m * 128 + ((((k >> 3) ^ (m & 7)) << 4) | ((k & 7) << 1));
-                    else dst = sm + C::OFF_A2T + ((k - 64) >> 3) * C::A2T_LBO + (m >> 3) * C::A2T_SBO + (m & 7) * 16 + ((k - 64) & 7) * 2;
-                    *reinterpret_cast<uint32_t*>(dst) = val;
+                    if (u < 8) dst = sm + C::OFF_A2 + m * 128 + ((u ^ (m & 7)) << 4);
+                    else dst = sm + C::OFF_A2T + (u - 8) * C::A2T_LBO + (m >> 3) * C::A2T_SBO + (m & 7) * 16;
+                    if (u == U0) {
+                        if (C::HID % 8 == 0) *reinterpret_cast<uint4*>(dst) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+                        else *reinterpret_cast<uint2*>(dst + 8) = make_uint2(0x00003F80u, 0u);
+                    } else {
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
             }
         }
@@ -457,6 +499,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
 
         // ---------------- P5: GEMM2 (accumulators reuse GEMM1's TMEM columns) ----------------
         if (tid == 0) {
+            if (next < p.total) load_x(par ^ 1);        // region X is free: the depthwise phase has consumed the hidden tile
             tc_fence_after_sync();
             for (int t = 0; t < C::M2T; ++t) {
 #pragma unroll
@@ -468,11 +511,6 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                     umma_bf16(tmem + t * C::N2, da, db, IDESC2, s > 0);
                 }
                 umma_commit(bar_mma2 + t);
-            }
-            // region Y is free once GEMM2 has read A2: request the next patch's x tile
-            if (next < p.total) {
-                for (int t = 0; t < C::M2T; ++t) mbar_wait(bar_mma2 + t, par);
-                load_x(par ^ 1);
             }
         }
 
