@@ -172,6 +172,15 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(tag: str):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(REPO, "profiles", "r01_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"][tag])
+    except Exception:
+        return None
+
+
 def kernel_rooflines(batch: int, iters: int = 12):
     """Time each decoder kernel of HyperSeg-M alone at its real shape.  Inputs rotate over 3 buffer sets so that a
     launch never finds its operands in L2 (one set of the level-4 kernel alone is 146 MB > 126 MB L2)."""
@@ -385,7 +394,9 @@ def run_ours(args):
             "wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"kernel": "hsb_patch_ir_fwd @ decoder level 4 (B x 34 x 256 x 512 -> 19 ch, 16x16 patches)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": top["bytes"],
+                         "traffic": ncu_traffic("ir") if B == 8 else None,
+                         "traffic_source": "profiles/r01_traffic.json (ncu --set full: dram read + write bytes per launch)",
+                         "peak_source": peak_src, "bytes_per_launch": top["bytes"],
                          "ms_per_launch": top["ms"]},
             "patch_conv": agg(conv_keys), "heads": agg(head_keys), "whole_box": whole_box,
             "kernels": {k: {"ms": round(v["ms"], 5), "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)}
