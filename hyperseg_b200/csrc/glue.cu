@@ -33,6 +33,7 @@ __device__ __forceinline__ BilinearAxis bilinear_axis(int dst, int in, float sca
 struct DecInParams {
     const void* coords; const void* feat; const void* prev; void* out;
     int B, Cc, Cf, Cp, H, W, h, w;
+    int out_channels;                // channel count of `out` (== Cc + Cf + Cp unless the upsampled part is done elsewhere)
     int64_t fsb, fsc, fsy, fsx;      // feature strides (elements): NCHW or NHWC
     float sy, sx;                    // h/H, w/W
 };
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) decoder_input_kernel(const DecInParams p)
                 }
             }
         }
-        T* dst = out + (((size_t)b * C + c) * p.H + y) * p.W + x0;
+        T* dst = out + (((size_t)b * p.out_channels + c) * p.H + y) * p.W + x0;
         if (n == 8 && sizeof(T) == 2 && (p.W % 8) == 0) {
             __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
             __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
@@ -139,6 +140,116 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(const TailParams p
     }
 }
 
+// ---- exact 2x upsampling (every decoder level and the logit tail): fixed taps, vector loads ----------------------------------
+// For out = 2*in, align_corners=False:  out[2j] = 0.25*in[j-1] + 0.75*in[j],  out[2j+1] = 0.75*in[j] + 0.25*in[j+1]  (indices
+// clamped to the border; at the border the two taps coincide, which reproduces ATen's src = max(src, 0) / i1 = min(i0+1, in-1)).
+// A thread takes source rows (i, i+1) and 4 source columns c0..c0+3 (+ one neighbour each side) and produces the 2 x 8 output
+// pixels (rows 2i+1, 2i+2; columns 2*c0 .. 2*c0+7) that depend on them.
+
+__device__ __forceinline__ void load_row6(const __nv_bfloat16* row, int c0, int w, float (&s)[6]) {
+    // s[0..5] = in[c0-1 .. c0+4], clamped; c0 % 4 == 0 and w % 4 == 0 -> the middle four are one aligned 8-byte load
+    const uint2 mid = *reinterpret_cast<const uint2*>(row + c0);
+    const __nv_bfloat162 m0 = *reinterpret_cast<const __nv_bfloat162*>(&mid.x), m1 = *reinterpret_cast<const __nv_bfloat162*>(&mid.y);
+    s[1] = __low2float(m0); s[2] = __high2float(m0); s[3] = __low2float(m1); s[4] = __high2float(m1);
+    s[0] = c0 > 0 ? __bfloat162float(row[c0 - 1]) : s[1];
+    s[5] = c0 + 4 < w ? __bfloat162float(row[c0 + 4]) : s[4];
+}
+
+__device__ __forceinline__ void hinterp8(const float (&s)[6], float (&o)[8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o[2 * j] = 0.25f * s[j] + 0.75f * s[j + 1];           // ATen: w0*p0 + w1*p1 with (w0, w1) = (0.25, 0.75)
+        o[2 * j + 1] = 0.75f * s[j + 1] + 0.25f * s[j + 2];
+    }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_argmax_kernel(const TailParams p) {
+    const int segs = p.w / 4;
+    const size_t total = (size_t)p.B * (p.h + 1) * segs;
+    const __nv_bfloat16* lg = reinterpret_cast<const __nv_bfloat16*>(p.logits);
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int sg = idx % segs;
+        const int i = (int)((idx / segs) % (p.h + 1)) - 1;          // source row pair (i, i+1), i = -1 .. h-1
+        const int b = idx / ((size_t)segs * (p.h + 1));
+        const int r0 = max(i, 0), r1 = min(i + 1, p.h - 1), c0 = sg * 4;
+        float best1[8], best2[8];
+        int arg1[8], arg2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { best1[e] = best2[e] = -INFINITY; arg1[e] = arg2[e] = 0; }
+        for (int c = 0; c < p.C; ++c) {
+            const __nv_bfloat16* base = lg + ((size_t)b * p.C + c) * p.h * p.w;
+            float s0[6], s1[6], h0[8], h1[8];
+            load_row6(base + (size_t)r0 * p.w, c0, p.w, s0);
+            load_row6(base + (size_t)r1 * p.w, c0, p.w, s1);
+            hinterp8(s0, h0);
+            hinterp8(s1, h1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                // the reference rounds the upsampled logits to bf16 before argmax
+                const float v1 = __bfloat162float(__float2bfloat16_rn(0.75f * h0[e] + 0.25f * h1[e]));   // row 2i+1
+                const float v2 = __bfloat162float(__float2bfloat16_rn(0.25f * h0[e] + 0.75f * h1[e]));   // row 2i+2
+                if (v1 > best1[e]) { best1[e] = v1; arg1[e] = c; }
+                if (v2 > best2[e]) { best2[e] = v2; arg2[e] = c; }
+            }
+        }
+        const int y1 = 2 * i + 1, y2 = 2 * i + 2;
+        if (y1 >= 0) {
+            uint2 pk;
+            pk.x = arg1[0] | (arg1[1] << 8) | (arg1[2] << 16) | (arg1[3] << 24);
+            pk.y = arg1[4] | (arg1[5] << 8) | (arg1[6] << 16) | (arg1[7] << 24);
+            *reinterpret_cast<uint2*>(p.labels + ((size_t)b * p.H + y1) * p.W + 2 * c0) = pk;
+        }
+        if (y2 < p.H) {
+            uint2 pk;
+            pk.x = arg2[0] | (arg2[1] << 8) | (arg2[2] << 16) | (arg2[3] << 24);
+            pk.y = arg2[4] | (arg2[5] << 8) | (arg2[6] << 16) | (arg2[7] << 24);
+            *reinterpret_cast<uint2*>(p.labels + ((size_t)b * p.H + y2) * p.W + 2 * c0) = pk;
+        }
+    }
+}
+
+// upsampled channels of the level input (bf16, exact 2x): out[b, c_off + cp, 2i+1 / 2i+2, 8 px]
+__global__ void __launch_bounds__(256) decoder_prev2x_kernel(const DecInParams p) {
+    const int segs = p.w / 4;
+    const size_t total = (size_t)p.B * p.Cp * (p.h + 1) * segs;
+    const int C = p.Cc + p.Cf + p.Cp;
+    const __nv_bfloat16* prev = reinterpret_cast<const __nv_bfloat16*>(p.prev);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int sg = idx % segs;
+        const int i = (int)((idx / segs) % (p.h + 1)) - 1;
+        const int cp = (idx / ((size_t)segs * (p.h + 1))) % p.Cp;
+        const int b = idx / ((size_t)segs * (p.h + 1) * p.Cp);
+        const int r0 = max(i, 0), r1 = min(i + 1, p.h - 1), c0 = sg * 4;
+        const __nv_bfloat16* base = prev + ((size_t)b * p.Cp + cp) * p.h * p.w;
+        float s0[6], s1[6], h0[8], h1[8];
+        load_row6(base + (size_t)r0 * p.w, c0, p.w, s0);
+        load_row6(base + (size_t)r1 * p.w, c0, p.w, s1);
+        hinterp8(s0, h0);
+        hinterp8(s1, h1);
+        __nv_bfloat16* o = out + (((size_t)b * C + p.Cc + p.Cf + cp) * p.H) * p.W + 2 * c0;
+        const int y1 = 2 * i + 1, y2 = 2 * i + 2;
+        if (y1 >= 0) {
+            uint32_t q[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(0.75f * h0[2 * e] + 0.25f * h1[2 * e], 0.75f * h0[2 * e + 1] + 0.25f * h1[2 * e + 1]);
+                q[e] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(o + (size_t)y1 * p.W) = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+        if (y2 < p.H) {
+            uint32_t q[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(0.25f * h0[2 * e] + 0.75f * h1[2 * e], 0.25f * h0[2 * e + 1] + 0.75f * h1[2 * e + 1]);
+                q[e] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(o + (size_t)y2 * p.W) = make_uint4(q[0], q[1], q[2], q[3]);
+        }
+    }
+}
+
 }  // namespace hsb
 
 using namespace hsb;
@@ -156,11 +267,30 @@ extern "C" int hsb_decoder_input_fwd(const void* coords, const void* feature, co
     DecInParams p;
     p.coords = coords; p.feat = feature; p.prev = prev; p.out = out;
     p.B = B; p.Cc = Cc; p.Cf = Cf; p.Cp = Cp; p.H = H; p.W = W; p.h = Cp ? h : 1; p.w = Cp ? w : 1;
+    p.out_channels = Cc + Cf + Cp;
     p.fsb = f_stride_b; p.fsc = f_stride_c; p.fsy = f_stride_y; p.fsx = f_stride_x;
     p.sy = (float)p.h / (float)H; p.sx = (float)p.w / (float)W;
-    const size_t total = (size_t)B * (Cc + Cf + Cp) * H * ((W + 7) / 8);
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)std::max(1, device_sm_count()) * 32);
     cudaStream_t st = (cudaStream_t)stream;
+    const int cap = std::max(1, device_sm_count()) * 32;
+    // exact 2x upsampling of bf16 maps (every level of the shipped decoders): fixed-tap vector kernel for the
+    // upsampled channels, the generic kernel then only copies coords + feature
+    const bool fast2x = dtype == HSB_BF16 && Cp > 0 && H == 2 * p.h && W == 2 * p.w && (p.w % 4) == 0 &&
+                        ((uintptr_t)prev % 16) == 0 && ((uintptr_t)out % 16) == 0;
+    if (fast2x) {
+        const size_t t2 = (size_t)B * Cp * (p.h + 1) * (p.w / 4);
+        decoder_prev2x_kernel<<<(int)std::min<size_t>((t2 + 255) / 256, cap), 256, 0, st>>>(p);
+        int rc = check_launch("decoder_prev2x launch");
+        if (rc != HSB_OK) return rc;
+        if (Cc + Cf == 0) return HSB_OK;
+        DecInParams q = p;
+        q.Cp = 0;                       // copy channels only; the output keeps its full channel count via out_channels
+        q.out_channels = Cc + Cf + Cp;
+        const size_t t1 = (size_t)B * (Cc + Cf) * H * ((W + 7) / 8);
+        decoder_input_kernel<__nv_bfloat16><<<(int)std::min<size_t>((t1 + 255) / 256, cap), 256, 0, st>>>(q);
+        return check_launch("decoder_input launch");
+    }
+    const size_t total = (size_t)B * (Cc + Cf + Cp) * H * ((W + 7) / 8);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, cap);
     if (dtype == HSB_F32) decoder_input_kernel<float><<<blocks, 256, 0, st>>>(p);
     else decoder_input_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
     return check_launch("decoder_input launch");
@@ -175,9 +305,15 @@ extern "C" int hsb_upsample_argmax_fwd(const void* logits, void* labels, int B, 
     TailParams p;
     p.logits = logits; p.labels = (unsigned char*)labels; p.B = B; p.C = C; p.h = h; p.w = w; p.H = H; p.W = W;
     p.sy = (float)h / (float)H; p.sx = (float)w / (float)W;
-    const size_t total = (size_t)B * H * ((W + 3) / 4);
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)std::max(1, device_sm_count()) * 32);
     cudaStream_t st = (cudaStream_t)stream;
+    const int cap = std::max(1, device_sm_count()) * 32;
+    if (dtype == HSB_BF16 && H == 2 * h && W == 2 * w && (w % 4) == 0 && ((uintptr_t)logits % 8) == 0 && ((uintptr_t)labels % 8) == 0) {
+        const size_t t2 = (size_t)B * (h + 1) * (w / 4);
+        upsample2x_argmax_kernel<<<(int)std::min<size_t>((t2 + 255) / 256, cap), 256, 0, st>>>(p);
+        return check_launch("upsample2x_argmax launch");
+    }
+    const size_t total = (size_t)B * H * ((W + 3) / 4);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, cap);
     if (dtype == HSB_F32) upsample_argmax_kernel<float><<<blocks, 256, 0, st>>>(p);
     else upsample_argmax_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
     return check_launch("upsample_argmax launch");
