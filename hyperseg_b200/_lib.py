@@ -45,6 +45,14 @@ SIGNATURES = {
                             c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int, c_int, c_void_p],
+    "hsb_patch_conv_bwd_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p],
+    "hsb_patch_conv_bwd_input": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p],
+    "hsb_signal2weights_bwd_signal": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_void_p],
+    "hsb_signal2weights_bwd_weight": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_void_p],
     "hsb_decoder_input_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_int64, c_int64, c_int64, c_int64, c_int, c_void_p],
     "hsb_upsample_argmax_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],

@@ -54,11 +54,17 @@ def _require_cuda(*tensors: torch.Tensor) -> None:
                 f"got a tensor on {t.device}")
 
 
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def _require_inference(*tensors: torch.Tensor) -> None:
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+    """For the operators that have no backward kernel (the fused inverted-residual block, the glue kernels)."""
+    if _needs_grad(*tensors):
         raise NotImplementedError(
-            "hyperseg_b200 implements the forward (inference) hot path only; backward kernels are not "
-            "built yet -- run under torch.no_grad() / model.eval()")
+            "this hyperseg_b200 operator is forward-only: gradients are implemented for the patch-wise convolutions "
+            "(MetaPatchConv2d / HyperPatchNoPadding / HyperPatchConv2d) and the weight heads, i.e. the hyperseg_v0_1 "
+            "training path; run the fused inverted-residual block under torch.no_grad() / model.eval()")
 
 
 def _stream() -> int:
@@ -129,7 +135,6 @@ def fold_bn(bn: torch.nn.BatchNorm2d):
 
 def _prep_xw(x, w):
     _require_cuda(x, w)
-    _require_inference(x, w)
     dt = _compute_dtype(x)
     x = x.to(dt).contiguous()
     if w.dtype != dt:
@@ -140,8 +145,25 @@ def _prep_xw(x, w):
     return x, w, layout, row, dt
 
 
+def _unfused_epilogue(y, scale, shift, act):
+    if scale is not None:
+        y = y * scale.to(y.dtype).view(1, -1, 1, 1) + shift.to(y.dtype).view(1, -1, 1, 1)
+    if act == "relu":
+        y = torch.relu(y)
+    elif act == "relu6":
+        y = torch.nn.functional.relu6(y)
+    return y
+
+
 def patch_conv1x1(x, w, out_channels, groups=1, scale=None, shift=None, act="none"):
     """Patch-wise 1x1 convolution (+ fused per-channel affine and activation)."""
+    if _needs_grad(x, w, scale, shift):
+        y = _PatchConvFn.apply(x, w, out_channels, (1, 1), (0, 0), (1, 1), groups, "zeros")
+        return _unfused_epilogue(y, scale, shift, act)
+    return _patch_conv1x1_fwd(x, w, out_channels, groups, scale, shift, act)
+
+
+def _patch_conv1x1_fwd(x, w, out_channels, groups=1, scale=None, shift=None, act="none"):
     x, w, layout, row, dt = _prep_xw(x, w)
     B, Cin, H, W = x.shape
     hp = out_channels * (Cin // groups)
@@ -157,6 +179,7 @@ def patch_conv1x1(x, w, out_channels, groups=1, scale=None, shift=None, act="non
 
 def patch_ir(x, w, hidden, out_channels, bn1, bn2, bn3, residual=False):
     """Fused patch-wise inverted residual block; bn* are (scale, shift) pairs of the folded BatchNorms."""
+    _require_inference(x, w)
     x, w, layout, row, dt = _prep_xw(x, w)
     B, Cin, H, W = x.shape
     hp = Cin * hidden + 9 * hidden + hidden * out_channels
@@ -198,8 +221,13 @@ def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
 
     ``ws`` is the nn.Conv2d weight (out_ch, sig_ch/groups, 1, 1); only the first ``hp`` output channels
     are produced (the reference computes all ``out_ch`` and slices)."""
+    if _needs_grad(s, ws):
+        return _HeadFn.apply(s, ws, sig_index, sig_ch, hp, groups)
+    return _signal2weights_fwd(s, ws, sig_index, sig_ch, hp, groups)
+
+
+def _signal2weights_fwd(s, ws, sig_index, sig_ch, hp, groups):
     _require_cuda(s, ws)
-    _require_inference(s, ws)
     dt = _compute_dtype(s)
     if s.dtype != dt:
         s = s.to(dt)
@@ -235,6 +263,14 @@ def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
 def patch_conv(x, w, out_channels, kernel_size, padding, dilation=(1, 1), groups=1, padding_mode="reflect",
                scale=None, shift=None, act="none"):
     """General patch-wise convolution (MetaPatchConv2d / HyperPatchConv2d semantics)."""
+    if _needs_grad(x, w, scale, shift):
+        y = _PatchConvFn.apply(x, w, out_channels, tuple(kernel_size), tuple(padding), tuple(dilation), groups, padding_mode)
+        return _unfused_epilogue(y, scale, shift, act)
+    return _patch_conv_fwd(x, w, out_channels, kernel_size, padding, dilation, groups, padding_mode, scale, shift, act)
+
+
+def _patch_conv_fwd(x, w, out_channels, kernel_size, padding, dilation=(1, 1), groups=1, padding_mode="reflect",
+                    scale=None, shift=None, act="none"):
     x, w, layout, row, dt = _prep_xw(x, w)
     B, Cin, H, W = x.shape
     kh, kw = kernel_size
@@ -323,3 +359,72 @@ def upsample_argmax(logits, size):
     labels = torch.empty((B, H, W), dtype=torch.uint8, device=logits.device)
     _call("hsb_upsample_argmax_fwd", logits.data_ptr(), labels.data_ptr(), B, C, h, w, H, W, _DTYPES[dt], _stream())
     return labels
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training path: autograd Functions over the backward entry points (hyperseg_v0_1 / BASELINE config 4)
+# ---------------------------------------------------------------------------------------------------------------------
+class _PatchConvFn(torch.autograd.Function):
+    """Patch-wise convolution with gradients for x and the per-patch weights (any kernel / groups / dilation / pad mode)."""
+
+    @staticmethod
+    def forward(ctx, x, w, out_channels, kernel_size, padding, dilation, groups, padding_mode):
+        xp, wp, layout, row, dt = _prep_xw(x, w)
+        if kernel_size == (1, 1) and padding == (0, 0):
+            y = _patch_conv1x1_fwd(xp, wp, out_channels, groups)
+        else:
+            y = _patch_conv_fwd(xp, wp, out_channels, kernel_size, padding, dilation, groups, padding_mode)
+        ctx.save_for_backward(xp, wp)
+        ctx.meta = (out_channels, kernel_size, padding, dilation, groups, padding_mode, layout, row, dt)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, wp = ctx.saved_tensors
+        out_channels, (kh, kw), (ph_, pw_), (dh, dw_), groups, mode, layout, row, dt = ctx.meta
+        dy = dy.to(dt).contiguous()
+        B, Cin, H, W = xp.shape
+        hp, fh, fw = wp.shape[1], wp.shape[2], wp.shape[3]
+        geom = (B, Cin, out_channels, H, W, fh, fw, kh, kw, ph_, pw_, dh, dw_, groups, PAD_MODES[mode], _DTYPES[dt], layout, row)
+        dx = dwt = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(xp)
+            _call("hsb_patch_conv_bwd_input", wp.data_ptr(), dy.data_ptr(), dx.data_ptr(), *geom, _stream())
+        if ctx.needs_input_grad[1]:
+            if layout == W_PATCH_MAJOR:
+                buf = torch.zeros((B, fh, fw, row), dtype=dt, device=xp.device)
+                dwt = buf[..., :hp].permute(0, 3, 1, 2)
+            else:
+                buf = dwt = torch.empty((B, hp, fh, fw), dtype=dt, device=xp.device)
+            _call("hsb_patch_conv_bwd_weight", xp.data_ptr(), dy.data_ptr(), buf.data_ptr(), *geom, _stream())
+        return dx, dwt, None, None, None, None, None, None
+
+
+class _HeadFn(torch.autograd.Function):
+    """signal -> per-patch weights head with gradients for the signal map and the static head weights."""
+
+    @staticmethod
+    def forward(ctx, s, ws, sig_index, sig_ch, hp, groups):
+        dt = _compute_dtype(s)
+        sp = s.detach().to(dt).contiguous()
+        out = _signal2weights_fwd(sp, ws.detach(), sig_index, sig_ch, hp, groups)
+        ctx.save_for_backward(sp, ws.detach().to(dt).reshape(ws.shape[0], -1).contiguous())
+        ctx.meta = (sig_index, sig_ch, hp, groups, dt, tuple(ws.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dwout):
+        sp, ws2 = ctx.saved_tensors
+        sig_index, sig_ch, hp, groups, dt, ws_shape = ctx.meta
+        B, C, fh, fw = sp.shape
+        g, layout, row = weight_layout(dwout.to(dt))
+        geom = (B, C, sig_index, sig_ch, ws2.shape[0], hp, groups, fh, fw, C * fh * fw, fh * fw, 1, _DTYPES[dt], layout, row)
+        ds = dws = None
+        if ctx.needs_input_grad[0]:
+            ds = torch.empty_like(sp)
+            _call("hsb_signal2weights_bwd_signal", ws2.data_ptr(), g.data_ptr(), ds.data_ptr(), *geom, _stream())
+        if ctx.needs_input_grad[1]:
+            dws = torch.empty_like(ws2)
+            _call("hsb_signal2weights_bwd_weight", sp.data_ptr(), g.data_ptr(), dws.data_ptr(), *geom, _stream())
+            dws = dws.reshape(ws_shape)
+        return ds, dws, None, None, None, None

@@ -154,6 +154,34 @@ int hsb_meta_conv2d_fwd(const void* x, const void* w, void* y,
                         int pad_mode, int dtype, void* stream);
 
 /*
+ * Training path (BASELINE config 4 = HyperSeg-L / hyperseg_v0_1 training step): gradients of
+ * hsb_patch_conv_fwd (and of the 1x1 kernel, with kh = kw = 1, pad 0) and of the weight head.  In the reference these
+ * come from autograd through F.pad / F.unfold / F.conv2d(groups) / F.fold (hyperseg/models/layers/meta_patch.py:35-57,
+ * meta_conv.py:163-186) and through the grouped nn.Conv2d of the heads (hyperseg_v0_1.py:336-362, hyperseg_v1_0.py:315-326).
+ *   hsb_patch_conv_bwd_weight   dw (same layout / row stride as w) from x and dy
+ *   hsb_patch_conv_bwd_input    dx from w and dy (gathers across patch borders and padding aliases; no atomics)
+ *   hsb_signal2weights_bwd_signal   ds (B, sig_total, fh, fw) with the given strides; channels outside the head's slice get 0
+ *   hsb_signal2weights_bwd_weight   dws (out_ch, sig_ch/G) contiguous; rows >= hp get 0
+ * `dwout` is the gradient of the head's output in `g_layout` (HSB_W_PATCH_MAJOR rows are g_row_stride apart).
+ */
+int hsb_patch_conv_bwd_weight(const void* x, const void* dy, void* dw,
+                              int B, int Cin, int Cout, int H, int W, int fh, int fw,
+                              int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, int groups,
+                              int pad_mode, int dtype, int w_layout, int64_t w_row_stride, void* stream);
+int hsb_patch_conv_bwd_input(const void* w, const void* dy, void* dx,
+                             int B, int Cin, int Cout, int H, int W, int fh, int fw,
+                             int kh, int kw, int pad_h, int pad_w, int dil_h, int dil_w, int groups,
+                             int pad_mode, int dtype, int w_layout, int64_t w_row_stride, void* stream);
+int hsb_signal2weights_bwd_signal(const void* ws, const void* dwout, void* ds,
+                                  int B, int sig_total, int sig_index, int sig_ch, int out_ch, int hp, int groups,
+                                  int fh, int fw, int64_t ds_stride_b, int64_t ds_stride_c, int64_t ds_stride_p,
+                                  int dtype, int g_layout, int64_t g_row_stride, void* stream);
+int hsb_signal2weights_bwd_weight(const void* s, const void* dwout, void* dws,
+                                  int B, int sig_total, int sig_index, int sig_ch, int out_ch, int hp, int groups,
+                                  int fh, int fw, int64_t s_stride_b, int64_t s_stride_c, int64_t s_stride_p,
+                                  int dtype, int g_layout, int64_t g_row_stride, void* stream);
+
+/*
  * Decoder glue, one pass: out = cat(coords, feature, bilinear_upsample(prev, (H, W)))  along channels.
  *   coords  (1, Cc, H, W) contiguous, broadcast over the batch (may be NULL with Cc == 0)
  *   feature (B, Cf, H, W) with arbitrary element strides (NCHW or NHWC)

@@ -30,6 +30,13 @@ _ACT = {
 
 
 # ---- padding by index arithmetic (reference: F.pad(..., mode), hyperseg_v1_0.py:337, meta_patch.py:50) ----
+def _in(t):
+    """Inputs are detached unless a gradient is being taken through the oracle (training-path tests)."""
+    if torch.is_grad_enabled() and t.requires_grad:
+        return t.to(DTYPE)
+    return t.detach().to(DTYPE)
+
+
 def _source_index(n, pad, mode):
     """For coordinates -pad .. n+pad-1: source index in [0, n) and validity mask."""
     i = torch.arange(-pad, n + pad)
@@ -103,7 +110,7 @@ def fold_bn(bn):
 # ---- a1: HyperPatchNoPadding.forward, hyperseg_v1_0.py:486-498 ------------------------------------------
 def patch_conv1x1(x, w, out_channels, groups=1, scale=None, shift=None, act="none"):
     out_dtype = x.dtype
-    x, w = x.detach().to(DTYPE), w.detach().to(DTYPE)
+    x, w = _in(x), _in(w)
     B, Cin, H, W = x.shape
     fh, fw = w.shape[-2:]
     ph, pw = H // fh, W // fw
@@ -117,7 +124,7 @@ def patch_conv1x1(x, w, out_channels, groups=1, scale=None, shift=None, act="non
 # ---- a2: HyperPatchInvertedResidual.conv / forward, hyperseg_v1_0.py:328-376 ----------------------------
 def patch_ir(x, w, hidden, out_channels, bn1, bn2, bn3, residual=False):
     out_dtype = x.dtype
-    x, w = x.detach().to(DTYPE), w.detach().to(DTYPE)
+    x, w = _in(x), _in(w)
     B, Cin, H, W = x.shape
     fh, fw = w.shape[-2:]
     ph, pw = H // fh, W // fw
@@ -147,7 +154,7 @@ def patch_ir(x, w, hidden, out_channels, bn1, bn2, bn3, residual=False):
 # ---- a3/a4/a8: signal2weights heads, hyperseg_v1_0.py:315-326; unify :287-309; v0_1 :336-362 --------------
 def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
     out_dtype = s.dtype
-    s, ws = s.detach().to(DTYPE), ws.detach().to(DTYPE)
+    s, ws = _in(s), _in(ws)
     B, _, fh, fw = s.shape
     out_ch = ws.shape[0]
     spg, opg = sig_ch // groups, out_ch // groups
@@ -161,7 +168,7 @@ def signal2weights(s, ws, sig_index, sig_ch, hp, groups):
 def patch_conv(x, w, out_channels, kernel_size, padding, dilation=(1, 1), groups=1, padding_mode="reflect",
                scale=None, shift=None, act="none"):
     out_dtype = x.dtype
-    x, w = x.detach().to(DTYPE), w.detach().to(DTYPE)
+    x, w = _in(x), _in(w)
     B, Cin, H, W = x.shape
     fh, fw = w.shape[-2:]
     ph, pw = H // fh, W // fw
@@ -185,7 +192,7 @@ def patch_conv(x, w, out_channels, kernel_size, padding, dilation=(1, 1), groups
 def meta_conv2d(x, w, out_channels, kernel_size, padding=(0, 0), dilation=(1, 1), groups=1, padding_mode="zeros"):
     """Per-sample dynamic convolution (meta_conv.py:163-186), stride 1."""
     out_dtype = x.dtype
-    x, w = x.detach().to(DTYPE), w.detach().to(DTYPE)
+    x, w = _in(x), _in(w)
     N, Cin, H, W = x.shape
     kh, kw = kernel_size
     cig, cog = Cin // groups, out_channels // groups

@@ -91,6 +91,29 @@ DIVIDE_CASES = [
 ]
 
 
+# gradient cases (training path): op cases whose inputs get requires_grad; loss = sum(y * r) with a seeded r
+GRAD_CASES = ["nopad_basic", "nopad_groups", "nopad_odd", "nopad_p1", "metapatch_pw", "metapatch_dw", "metapatch_dil",
+              "metapatch_circ", "metapatch_1patch", "hpconv_k3", "hpconv_k3_head", "block1x1_head", "mpblock_dw", "v01_ir_res"]
+# whole-model training step (BASELINE config 4 at a size the CPU finishes quickly): config, batch, H, W
+TRAIN_CASE = dict(config="hyperseg-l-voc", B=2, H=128, W=128, seed=5)
+TRAIN_PARAMS = ["weight_mapper.out_conv.conv_0.weight", "weight_mapper.out_conv.conv_5.weight", "weight_mapper.flat_0.0.weight",
+                "weight_mapper.down_0.0.weight", "decoder.level_0.0.1.weight", "decoder.level_2.0.conv.1.1.bias",
+                "decoder.level_5.0.conv.2.1.weight", "backbone._conv_stem.weight", "backbone._blocks.5._project_conv.weight",
+                "backbone._conv_head.weight"]
+
+
+def grad_probe(name, shape):
+    g = torch.Generator().manual_seed(case_seed(name) + 17)
+    return torch.randn(*shape, generator=g)
+
+
+def train_labels(case, num_classes):
+    g = torch.Generator().manual_seed(case["seed"])
+    lab = torch.randint(0, num_classes, (case["B"], case["H"], case["W"]), generator=g)
+    lab[:, :4, :] = 255            # some ignored pixels
+    return lab
+
+
 def case_seed(name):
     import zlib
     return zlib.crc32(name.encode()) % (2 ** 31 - 1)

@@ -11,6 +11,8 @@ seeded inputs.  Written files (all committed):
     tests/golden/models.npz   whole-model logits (spatial stride 2) of cases.MODEL_CASES, weights from
                               hyperseg_b200.synthetic.deterministic_init
     tests/golden/divide.npz   divide_feature / divide_feature_legacy results and per-config head geometry
+    tests/golden/grads.npz    reference autograd gradients of the op cases in cases.GRAD_CASES and of one
+                              HyperSeg-L (hyperseg_v0_1) training step (loss, parameter gradients, BN statistics)
 """
 import importlib
 import os
@@ -80,6 +82,45 @@ def main():
         print(f"{name:22s} s{tuple(s.shape)} -> w{tuple(wgt.shape)} conv_out={layer.signal2weights.out_channels}")
     np.savez_compressed(os.path.join(HERE, "ops.npz"), **ops)
 
+    # ---- gradients of the same modules (reference autograd), training path ----
+    torch.set_grad_enabled(True)
+    grads = {}
+    for name in cases.GRAD_CASES:
+        case = cases.OP_CASES[name]
+        m = cases.build_op_module(ns, case)
+        deterministic_init(m, cases.case_seed(name)).eval()
+        x, w = cases.op_inputs(name, case, m.hyper_params)
+        x.requires_grad_(True); w.requires_grad_(True)
+        y = m(x, w)
+        (y * cases.grad_probe(name, y.shape)).sum().backward()
+        grads[f"{name}/dx"], grads[f"{name}/dw"] = x.grad.numpy(), w.grad.numpy()
+        for pn, pp in m.named_parameters():
+            if pn.endswith("signal2weights.weight"):
+                grads[f"{name}/dhead"] = pp.grad.numpy()
+        print(f"grad {name:20s} |dx|={x.grad.abs().max():.3f} |dw|={w.grad.abs().max():.3f}")
+
+    tc = cases.TRAIN_CASE
+    cfg = CONFIGS[tc["config"]]
+    mod = importlib.import_module("hyperseg.models." + cfg["module"])
+    kwargs = {k: (list(v) if isinstance(v, list) else v) for k, v in cfg["kwargs"].items()}
+    model = mod.hyperseg_efficientnet(cfg["model_name"], pretrained=False, num_classes=cfg["num_classes"], **kwargs)
+    deterministic_init(model, 0).train()
+    x = synthetic_frames(tc["B"], tc["H"], tc["W"])
+    labels = cases.train_labels(tc, cfg["num_classes"])
+    torch.manual_seed(tc["seed"])                     # drop-connect masks
+    loss = torch.nn.functional.cross_entropy(model(x), labels, ignore_index=255)
+    loss.backward()
+    grads["train/loss"] = np.array([loss.item()], dtype=np.float64)
+    named = dict(model.named_parameters())
+    for pn in cases.TRAIN_PARAMS:
+        g = named[pn].grad
+        grads[f"train/{pn}/norm"] = np.array([g.double().norm().item()])
+        grads[f"train/{pn}/head"] = g.flatten()[:64].numpy()
+    grads["train/bn_mean"] = dict(model.named_buffers())["decoder.level_0.0.1.running_mean"].numpy()
+    print(f"train step loss={loss.item():.6f}")
+    np.savez_compressed(os.path.join(HERE, "grads.npz"), **grads)
+    torch.set_grad_enabled(False)
+
     models = {}
     geometry = {}
     for name, mc_ in cases.MODEL_CASES.items():
@@ -124,7 +165,7 @@ def main():
             div[f"legacy/{i}"] = np.array([-1], dtype=np.int64)
     div.update({"geometry/" + k: v for k, v in geometry.items()})
     np.savez_compressed(os.path.join(HERE, "divide.npz"), **div)
-    for f in ("ops.npz", "models.npz", "divide.npz"):
+    for f in ("ops.npz", "models.npz", "divide.npz", "grads.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

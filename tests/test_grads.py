@@ -1,0 +1,130 @@
+"""Training path (BASELINE config 4): gradients against the reference's autograd.
+
+tests/golden/grads.npz holds gradients produced by the unmodified reference (make_golden.py).  On CPU the
+differentiable oracle is checked against them (this also pins the host-side autograd plumbing of the mirror
+modules); on the GPU (-m gpu) the CUDA backward kernels, reached through torch.autograd.Function wrappers in
+hyperseg_b200.ops, are checked against the same vectors -- op by op, and for one whole HyperSeg-L training step
+(loss, parameter gradients of heads / weight mapper / decoder BatchNorms / encoder, BatchNorm running statistics).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import GOLDEN, mirror_namespace, rel_err
+from hyperseg_b200.synthetic import CONFIGS, build_model, deterministic_init, synthetic_frames
+from oracle import hyperseg_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def golden_grads():
+    return np.load(os.path.join(GOLDEN, "grads.npz"))
+
+
+def _run_case(name, device):
+    case = cases.OP_CASES[name]
+    m = cases.build_op_module(mirror_namespace(), case)
+    deterministic_init(m, cases.case_seed(name)).eval().to(device)
+    x, w = cases.op_inputs(name, case, m.hyper_params)
+    x = x.to(device).requires_grad_(True)
+    w = w.to(device).requires_grad_(True)
+    y = m(x, w)
+    (y * cases.grad_probe(name, y.shape).to(device)).sum().backward()
+    head = [p.grad for n, p in m.named_parameters() if n.endswith("signal2weights.weight")]
+    return x.grad, w.grad, (head[0] if head else None)
+
+
+@pytest.mark.parametrize("name", cases.GRAD_CASES)
+def test_oracle_gradients_match_reference(name, golden_grads):
+    with orc.use_oracle_ops():
+        dx, dw, dhead = _run_case(name, "cpu")
+    assert rel_err(dx, golden_grads[f"{name}/dx"]) < 5e-6
+    assert rel_err(dw, golden_grads[f"{name}/dw"]) < 5e-6
+    if dhead is not None:
+        assert rel_err(dhead, golden_grads[f"{name}/dhead"]) < 5e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", cases.GRAD_CASES)
+def test_cuda_gradients_match_reference(name, golden_grads):
+    dx, dw, dhead = _run_case(name, "cuda")
+    assert rel_err(dx.cpu(), golden_grads[f"{name}/dx"]) < 2e-5
+    assert rel_err(dw.cpu(), golden_grads[f"{name}/dw"]) < 2e-5
+    if dhead is not None:
+        assert rel_err(dhead.cpu(), golden_grads[f"{name}/dhead"]) < 2e-5
+
+
+def _train_step(device):
+    tc = cases.TRAIN_CASE
+    cfg = CONFIGS[tc["config"]]
+    model = build_model(tc["config"], seed=0).train().to(device)
+    x = synthetic_frames(tc["B"], tc["H"], tc["W"]).to(device)
+    labels = cases.train_labels(tc, cfg["num_classes"]).to(device)
+    torch.manual_seed(tc["seed"])
+    loss = torch.nn.functional.cross_entropy(model(x), labels, ignore_index=255)
+    loss.backward()
+    return model, loss
+
+
+def _check_train(model, loss, golden, tol, loss_tol=1e-5):
+    # the loss agrees to ~1e-7; parameter gradients go through train-mode BatchNorm with a batch of 2 at 1x1..4x4
+    # resolution, which amplifies fp32 rounding differences to ~3e-3 between two correct implementations
+    assert abs(loss.item() - golden["train/loss"][0]) < loss_tol * abs(golden["train/loss"][0])
+    named = dict(model.named_parameters())
+    for pn in cases.TRAIN_PARAMS:
+        g = named[pn].grad
+        assert g is not None, pn
+        ref_norm = golden[f"train/{pn}/norm"][0]
+        assert abs(g.double().norm().item() - ref_norm) < tol * ref_norm, pn
+        ref_head = torch.from_numpy(golden[f"train/{pn}/head"])
+        assert (g.flatten()[:64].cpu() - ref_head).abs().max().item() < tol * max(ref_head.abs().max().item(), 1e-3 * ref_norm), pn
+    mean = dict(model.named_buffers())["decoder.level_0.0.1.running_mean"]
+    assert rel_err(mean.cpu(), golden["train/bn_mean"]) < tol
+
+
+def test_oracle_training_step_matches_reference(golden_grads):
+    with orc.use_oracle_ops():
+        model, loss = _train_step("cpu")
+    _check_train(model, loss, golden_grads, 1e-2)
+
+
+@pytest.mark.gpu
+def test_cuda_training_step_matches_reference(golden_grads):
+    """One HyperSeg-L (hyperseg_v0_1) training step on the CUDA forward + backward kernels, fp32."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        model, loss = _train_step("cuda")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    _check_train(model, loss, golden_grads, 2e-2, loss_tol=1e-4)
+
+
+@pytest.mark.gpu
+def test_cuda_training_step_bf16_autocast_runs_and_is_close(golden_grads):
+    tc = cases.TRAIN_CASE
+    cfg = CONFIGS[tc["config"]]
+    model = build_model(tc["config"], seed=0).train().cuda()
+    x = synthetic_frames(tc["B"], tc["H"], tc["W"]).cuda()
+    labels = cases.train_labels(tc, cfg["num_classes"]).cuda()
+    torch.manual_seed(tc["seed"])
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = torch.nn.functional.cross_entropy(model(x).float(), labels, ignore_index=255)
+    loss.backward()
+    assert abs(loss.item() - golden_grads["train/loss"][0]) < 3e-2 * golden_grads["train/loss"][0]
+    g = dict(model.named_parameters())["weight_mapper.out_conv.conv_0.weight"].grad
+    ref = golden_grads["train/weight_mapper.out_conv.conv_0.weight/norm"][0]
+    assert torch.isfinite(g).all() and abs(g.double().norm().item() - ref) < 0.15 * ref
+
+
+@pytest.mark.gpu
+def test_fused_ir_block_refuses_gradients():
+    from hyperseg_b200 import ops
+    x = torch.zeros(1, 4, 8, 8, device="cuda", requires_grad=True)
+    w = torch.zeros(1, 4 * 8 + 72 + 8 * 4, 1, 1, device="cuda")
+    bn = (torch.ones(8, device="cuda"), torch.zeros(8, device="cuda"))
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        ops.patch_ir(x, w, 8, 4, bn, bn, (torch.ones(4, device="cuda"), torch.zeros(4, device="cuda")))
