@@ -121,10 +121,16 @@ class MBConvBlock(nn.Module):
         if self.skip:
             if drop_connect_rate and self.training:
                 keep = 1 - drop_connect_rate
-                mask = torch.floor(keep + torch.rand([y.shape[0], 1, 1, 1], dtype=y.dtype, device=y.device))
+                mask = torch.floor(keep + _uniform_per_sample(y))
                 y = y / keep * mask
             y = y + x
         return y
+
+
+def _uniform_per_sample(y):
+    """One U[0,1) draw per batch element on y's device (drop-connect mask source; tests swap in a
+    CPU-generator version so masks match the reference's CPU run)."""
+    return torch.rand([y.shape[0], 1, 1, 1], dtype=y.dtype, device=y.device)
 
 
 class EfficientNet(nn.Module):

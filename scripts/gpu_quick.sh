@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python scripts/time_kernel.py ir 2>&1 | tail -1
-timeout 120 python scripts/time_kernel.py ir3 2>&1 | tail -1
-timeout 900 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider -x 2>&1 | tail -4
+timeout 600 python scripts/train_debug.py > gpurun_out/train_debug.log 2>&1
+timeout 600 python -m pytest tests/test_grads.py -m gpu -q 2>&1 | tail -15
