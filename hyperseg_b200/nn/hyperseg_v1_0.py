@@ -109,8 +109,32 @@ class HyperPatchInvertedResidual(nn.Module, _SignalHeadMixin):
     def _run(self, x, s, residual):
         self._check_supported()
         weight = self.apply_signal2weights(s)
+        if self.training or ops._needs_grad(x, weight):
+            y = self._run_stagewise(x, weight)
+            return x + y if residual else y
         return ops.patch_ir(x, weight, self.hidden_dim, self.out_nc, ops.fold_bn(self.bn1), ops.fold_bn(self.bn2),
                             ops.fold_bn(self.bn3), residual=residual)
+
+    def _run_stagewise(self, x, weight):
+        """Training path of the block (reference :328-368): the fused kernel has no backward and folds eval-mode
+        BatchNorms, so under autograd / train mode the three stages run as separate differentiable patch
+        convolutions around this module's own BatchNorms.  The halo tiles are laid out side by side as one
+        (fh*(ph+2)) x (fw*(pw+2)) map, which keeps the BatchNorm statistics those of the reference's
+        (b*fh*fw, C, ph+2, pw+2) view (same multiset of values per channel)."""
+        B, C, H, W = x.shape
+        fh, fw = weight.shape[-2:]
+        ph, pw = H // fh, W // fw
+        kh, kw = ph + 2, pw + 2
+        hid, r = self.hidden_dim, self._ranges
+        tiles = F.pad(x, self._padding_repeated_twice, mode=self.padding_mode).unfold(2, kh, ph).unfold(3, kw, pw)
+        h = tiles.permute(0, 1, 2, 4, 3, 5).reshape(B, C, fh * kh, fw * kw)                    # :342
+        h = self.act_layer(self.bn1(ops.patch_conv1x1(h, weight[:, r[0]:r[1]], hid)))           # :350-353
+        # depthwise on whole halo tiles with zero padding, keeping each tile's interior == the reference's
+        # unpadded ("valid") depthwise of :359
+        h = ops.patch_conv(h, weight[:, r[1]:r[2]], hid, (3, 3), (1, 1), (1, 1), hid, 'zeros')
+        h = h.reshape(B, hid, fh, kh, fw, kw)[:, :, :, 1:-1, :, 1:-1].reshape(B, hid, H, W)
+        h = self.act_layer(self.bn2(h))                                                         # :360-361
+        return self.bn3(ops.patch_conv1x1(h, weight[:, r[2]:r[3]], self.out_nc))                # :364-366
 
     def conv(self, x, s):
         return self._run(x, s, residual=False)

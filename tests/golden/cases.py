@@ -93,13 +93,26 @@ DIVIDE_CASES = [
 
 # gradient cases (training path): op cases whose inputs get requires_grad; loss = sum(y * r) with a seeded r
 GRAD_CASES = ["nopad_basic", "nopad_groups", "nopad_odd", "nopad_p1", "metapatch_pw", "metapatch_dw", "metapatch_dil",
-              "metapatch_circ", "metapatch_1patch", "hpconv_k3", "hpconv_k3_head", "block1x1_head", "mpblock_dw", "v01_ir_res"]
-# whole-model training step (BASELINE config 4 at a size the CPU finishes quickly): config, batch, H, W
+              "metapatch_circ", "metapatch_1patch", "hpconv_k3", "hpconv_k3_head", "block1x1_head", "mpblock_dw", "v01_ir_res",
+              "ir_small", "ir_res", "ir_head", "ir_rect"]
+# the same, with the module in train() mode (batch-statistics BatchNorm inside the block): y, dx, dw and the
+# updated running statistics of every BatchNorm are stored
+TRAIN_OP_CASES = ["ir_small", "ir_res", "ir_1patch", "ir_head", "block1x1", "mpblock_dw", "v01_ir"]
+# whole-model training steps at sizes the CPU finishes quickly: BASELINE config 4's model (HyperSeg-L VOC, hyperseg_v0_1)
+# and the north-star model (HyperSeg-M, hyperseg_v1_0: heads inside the layers, stage-wise inverted-residual blocks)
 TRAIN_CASE = dict(config="hyperseg-l-voc", B=2, H=128, W=128, seed=5)
 TRAIN_PARAMS = ["weight_mapper.out_conv.conv_0.weight", "weight_mapper.out_conv.conv_5.weight", "weight_mapper.flat_0.0.weight",
                 "weight_mapper.down_0.0.weight", "decoder.level_0.0.1.weight", "decoder.level_2.0.conv.1.1.bias",
                 "decoder.level_5.0.conv.2.1.weight", "backbone._conv_stem.weight", "backbone._blocks.5._project_conv.weight",
                 "backbone._conv_head.weight"]
+TRAIN_CASE_V10 = dict(config="hyperseg-m", B=2, H=128, W=256, seed=7)
+TRAIN_PARAMS_V10 = ["decoder.level_0.0.0.signal2weights.weight", "decoder.level_2.0.0.signal2weights.weight",
+                    "decoder.level_3.0.signal2weights.weight", "decoder.level_4.0.signal2weights.weight",
+                    "decoder.level_1.0.1.weight", "decoder.level_3.0.bn2.weight", "decoder.level_4.0.bn3.bias",
+                    "weight_mapper.in_conv.0.weight", "weight_mapper.in_conv.1.weight",
+                    "backbone._conv_stem.weight", "backbone._feat_fc_4.0.weight", "backbone._conv_head.weight"]
+TRAIN_STEPS = {"train": (TRAIN_CASE, TRAIN_PARAMS, "decoder.level_0.0.1.running_mean"),
+               "train_v10": (TRAIN_CASE_V10, TRAIN_PARAMS_V10, "decoder.level_4.0.bn1.running_mean")}
 
 
 def grad_probe(name, shape):

@@ -12,7 +12,8 @@ seeded inputs.  Written files (all committed):
                               hyperseg_b200.synthetic.deterministic_init
     tests/golden/divide.npz   divide_feature / divide_feature_legacy results and per-config head geometry
     tests/golden/grads.npz    reference autograd gradients of the op cases in cases.GRAD_CASES and of one
-                              HyperSeg-L (hyperseg_v0_1) training step (loss, parameter gradients, BN statistics)
+                              HyperSeg-L (hyperseg_v0_1) and one HyperSeg-M (hyperseg_v1_0) training step (loss, parameter
+                              gradients, BN statistics); blocks in train() mode
 """
 import importlib
 import os
@@ -99,25 +100,43 @@ def main():
                 grads[f"{name}/dhead"] = pp.grad.numpy()
         print(f"grad {name:20s} |dx|={x.grad.abs().max():.3f} |dw|={w.grad.abs().max():.3f}")
 
-    tc = cases.TRAIN_CASE
-    cfg = CONFIGS[tc["config"]]
-    mod = importlib.import_module("hyperseg.models." + cfg["module"])
-    kwargs = {k: (list(v) if isinstance(v, list) else v) for k, v in cfg["kwargs"].items()}
-    model = mod.hyperseg_efficientnet(cfg["model_name"], pretrained=False, num_classes=cfg["num_classes"], **kwargs)
-    deterministic_init(model, 0).train()
-    x = synthetic_frames(tc["B"], tc["H"], tc["W"])
-    labels = cases.train_labels(tc, cfg["num_classes"])
-    torch.manual_seed(tc["seed"])                     # drop-connect masks
-    loss = torch.nn.functional.cross_entropy(model(x), labels, ignore_index=255)
-    loss.backward()
-    grads["train/loss"] = np.array([loss.item()], dtype=np.float64)
-    named = dict(model.named_parameters())
-    for pn in cases.TRAIN_PARAMS:
-        g = named[pn].grad
-        grads[f"train/{pn}/norm"] = np.array([g.double().norm().item()])
-        grads[f"train/{pn}/head"] = g.flatten()[:64].numpy()
-    grads["train/bn_mean"] = dict(model.named_buffers())["decoder.level_0.0.1.running_mean"].numpy()
-    print(f"train step loss={loss.item():.6f}")
+    for name in cases.TRAIN_OP_CASES:
+        case = cases.OP_CASES[name]
+        m = cases.build_op_module(ns, case)
+        deterministic_init(m, cases.case_seed(name)).train()
+        x, w = cases.op_inputs(name, case, m.hyper_params)
+        x.requires_grad_(True); w.requires_grad_(True)
+        y = m(x, w)
+        (y * cases.grad_probe(name, y.shape)).sum().backward()
+        grads[f"{name}/train/y"] = y.detach().numpy()
+        grads[f"{name}/train/dx"], grads[f"{name}/train/dw"] = x.grad.numpy(), w.grad.numpy()
+        for bn, bb in m.named_buffers():
+            if bn.endswith("running_mean") or bn.endswith("running_var"):
+                grads[f"{name}/train/{bn}"] = bb.numpy().copy()
+        for pn, pp in m.named_parameters():
+            if pp.grad is not None:
+                grads[f"{name}/train/d_{pn}"] = pp.grad.numpy()
+        print(f"train-mode {name:14s} |y|={y.abs().max():.3f} |dx|={x.grad.abs().max():.3f} |dw|={w.grad.abs().max():.3f}")
+
+    for key, (tc, params, bn_name) in cases.TRAIN_STEPS.items():
+        cfg = CONFIGS[tc["config"]]
+        mod = importlib.import_module("hyperseg.models." + cfg["module"])
+        kwargs = {k: (list(v) if isinstance(v, list) else v) for k, v in cfg["kwargs"].items()}
+        model = mod.hyperseg_efficientnet(cfg["model_name"], pretrained=False, num_classes=cfg["num_classes"], **kwargs)
+        deterministic_init(model, 0).train()
+        x = synthetic_frames(tc["B"], tc["H"], tc["W"])
+        labels = cases.train_labels(tc, cfg["num_classes"])
+        torch.manual_seed(tc["seed"])                     # drop-connect / dropout masks
+        loss = torch.nn.functional.cross_entropy(model(x), labels, ignore_index=255)
+        loss.backward()
+        grads[f"{key}/loss"] = np.array([loss.item()], dtype=np.float64)
+        named = dict(model.named_parameters())
+        for pn in params:
+            g = named[pn].grad
+            grads[f"{key}/{pn}/norm"] = np.array([g.double().norm().item()])
+            grads[f"{key}/{pn}/head"] = g.flatten()[:64].numpy()
+        grads[f"{key}/bn_mean"] = dict(model.named_buffers())[bn_name].numpy()
+        print(f"{key} step ({tc['config']}) loss={loss.item():.6f} grad norms " + ' '.join(f"{named[pn].grad.norm().item():.2e}" for pn in params))
     np.savez_compressed(os.path.join(HERE, "grads.npz"), **grads)
     torch.set_grad_enabled(False)
 
