@@ -7,13 +7,15 @@ sm_100a without a GPU).
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import c_char_p, c_int, c_int64, c_void_p, POINTER
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libhsb200.so"
+# HSB_LIBRARY selects an experiment build of the same library (hyperseg_b200.build --variant); never a fallback
+LIB_PATH = Path(os.environ.get("HSB_LIBRARY") or (Path(__file__).resolve().parent / "libhsb200.so"))
 
 HSB_F32, HSB_BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SILU = 0, 1, 2, 3
 W_NCHW, W_PATCH_MAJOR = 0, 1
 PAD_MODES = {"zeros": 0, "reflect": 1, "replicate": 2, "circular": 3}
 
@@ -57,6 +59,9 @@ SIGNATURES = {
                               c_int64, c_int64, c_int64, c_int64, c_int, c_void_p],
     "hsb_upsample_argmax_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "hsb_weights_to_patch_major": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64, c_int, c_void_p],
+    "hsb_bias_act_nhwc_chunks": [c_int, c_int64, c_int],
+    "hsb_bias_act_nhwc_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p],
+    "hsb_channel_gate_nhwc_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p],
 }
 
 _lib = None

@@ -82,6 +82,31 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """Experiment builds (scripts/): libhsb200_<name>.so with extra -D flags, selected at run time with the
+    HSB_LIBRARY environment variable.  Not part of the product build."""
+    out_dir = BUILD_DIR / name
+    out_dir.mkdir(parents=True, exist_ok=True)
+    nvcc = _nvcc()
+    procs = []
+    for src in sources():
+        cmd = [nvcc, *ARCH_FLAGS, *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"], *[f"-D{d}" for d in defines],
+               "-I", str(INCLUDE), "-I", str(CSRC), "-c", str(src), "-o", str(out_dir / (src.stem + ".o"))]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            print(out)
+            raise RuntimeError("nvcc failed for variant " + name)
+    lib = PKG_DIR / f"libhsb200_{name}.so"
+    subprocess.run([nvcc, *ARCH_FLAGS, "-shared", "-Xcompiler", "-fPIC", "-o", str(lib),
+                    *[str(out_dir / (s.stem + ".o")) for s in sources()]], check=True)
+    return lib
+
+
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(path)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

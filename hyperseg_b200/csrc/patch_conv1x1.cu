@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) patch_conv1x1_kernel(const Conv1x1Params 
 
     // ---- stage weights ------------------------------------------------------------------
     if (p.bulk_ok) {
-        if (tid == 0) {
+        if ((tid >> 5) == 0 && elect_one()) {
             mbar_init(bar, 1);
             mbar_fence_init();
             const uint32_t row_bytes = (uint32_t)p.hp * sizeof(T);

@@ -111,6 +111,9 @@ struct IRTCParams {
     int64_t w_row_stride;      // elements between patch rows
     int w_bulk;                // rows are 16-byte aligned -> cp.async.bulk
     int total;                 // B * fh * fw
+#ifdef HSB_IR_PROF
+    long long* prof;           // [grid][10] per-phase cycle sums (profiling build only, scripts/ir_phase_prof.sh)
+#endif
 };
 
 __device__ __forceinline__ uint32_t pack_relu6(float lo, float hi) {
@@ -125,6 +128,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
+
+#ifdef HSB_IR_PROF
+#define HSB_STAMP(k) do { if (tid == 0) { long long now_ = clock64(); prof_acc[k] += now_ - prof_t; prof_t = now_; } } while (0)
+#else
+#define HSB_STAMP(k) do { } while (0)
+#endif
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
@@ -143,6 +152,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     uint64_t* bar_mma1 = bar_tma + 1;                     // [M1T] one per GEMM1 tile
     uint64_t* bar_mma2 = bar_mma1 + C::M1T;               // [M2T]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma2 + C::M2T);
+    uint64_t* bar_w = bar_tma + 7;                        // weight row of the patch (bar_tma then counts the x tile only)
     volatile int* coord = reinterpret_cast<volatile int*>(sm + C::OFF_COORD);
 
     const uint32_t a1_addr = smem_u32(sm + C::OFF_A1), b1_addr = smem_u32(sm + C::OFF_B1);
@@ -159,6 +169,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     for (int i = tid; i < C::COUT; i += C::THREADS) { s3[i] = p.bn[4][i]; b3[i] = p.bn[5][i]; }
     if (tid == 0) {
         mbar_init(bar_tma, 1);
+        mbar_init(bar_w, 1);
         for (int t = 0; t < C::M1T; ++t) mbar_init(bar_mma1 + t, 1);
         for (int t = 0; t < C::M2T; ++t) mbar_init(bar_mma2 + t, 1);
         mbar_fence_init();
@@ -173,18 +184,23 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     const int P = p.fh * p.fw;
     constexpr uint32_t X_BYTES = C::SZ_RAWX;
     constexpr uint32_t W_BYTES = r16(C::HP * 2);
-    // The loads of a patch are announced (expect_tx, coordinates) when its weight row is requested; the x tile is
-    // requested later, once its landing buffer (region Y) is free.  Both complete on bar_tma's current phase.
+    // A patch is announced (coordinates) when its weight row is requested; the x tile is requested later, once its
+    // landing buffer (region X) is free.  The weight row completes on bar_w, the x tile on bar_tma, so the weight
+    // re-stage of P1 runs while the x tile is still in flight.
     auto announce_and_load_w = [&](int patch, uint32_t slot) {         // one thread
         const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
         coord[slot * 4 + 0] = b; coord[slot * 4 + 1] = pi; coord[slot * 4 + 2] = pj;   // published by the arrive below
-        mbar_arrive_expect_tx(bar_tma, X_BYTES + (p.w_bulk ? W_BYTES : 0));
-        if (p.w_bulk) bulk_g2s(rawW, p.w + (size_t)patch * p.w_row_stride, W_BYTES, bar_tma);
+        if (p.w_bulk) {
+            mbar_arrive_expect_tx(bar_w, W_BYTES);
+            bulk_g2s(rawW, p.w + (size_t)patch * p.w_row_stride, W_BYTES, bar_w);
+        }
     };
-    auto load_x = [&](uint32_t slot) {                                 // one thread (the one that announced)
+    auto load_x = [&](uint32_t slot) {                                 // one thread, after the announcement is visible to it
+        mbar_arrive_expect_tx(bar_tma, X_BYTES);
         tma_load_4d(rawX, &xmap, coord[slot * 4 + 2] * C::PW - 8, coord[slot * 4 + 1] * C::PH - 1, 0, coord[slot * 4 + 0],
                     bar_tma);
     };
+    // in the loop an elected lane of warp 1 issues the loads while an elected lane of warp 0 issues the MMAs
     if (tid == 0 && (int)blockIdx.x < p.total) {
         announce_and_load_w(blockIdx.x, 0);
         load_x(0);
@@ -197,38 +213,48 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
     const int q = warp & 3;
     const int q_warps = (C::WARPS - q + 3) / 4, q_rank = warp >> 2;
 
+#ifdef HSB_IR_PROF
+    long long prof_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = clock64();
+#endif
     uint32_t it = 0;
     for (int patch = blockIdx.x; patch < p.total; patch += gridDim.x, ++it) {
         const uint32_t par = it & 1;
+        HSB_STAMP(9);
 
         // ---------------- P0: operands of this patch have landed ----------------
-        mbar_wait(bar_tma, par);
+        if (p.w_bulk) mbar_wait(bar_w, par); else mbar_wait(bar_tma, par);
+        HSB_STAMP(0);
         const int b = coord[par * 4 + 0], pi = coord[par * 4 + 1], pj = coord[par * 4 + 2];
         if (!p.w_bulk) {
             const __nv_bfloat16* src = p.w + (size_t)patch * p.w_row_stride;
             for (int k = tid; k < C::HP; k += C::THREADS) rawW[k] = src[k];
         }
         const bool left = pj == 0, right = pj == p.fw - 1, top = pi == 0, bottom = pi == p.fh - 1;
-        if (left || right) {                       // reflect: column -1 <- column 1, column W <- column W-2
-            for (int i = tid; i < C::CIN * C::TH; i += C::THREADS) {
-                __nv_bfloat16* row = rawX + (size_t)i * C::TWB + C::XOFF;
-                if (left) row[0] = row[2];
-                if (right) row[C::TW - 1] = row[C::TW - 3];
+        auto patch_halo = [&]() {
+            if (left || right) {                       // reflect: column -1 <- column 1, column W <- column W-2
+                for (int i = tid; i < C::CIN * C::TH; i += C::THREADS) {
+                    __nv_bfloat16* row = rawX + (size_t)i * C::TWB + C::XOFF;
+                    if (left) row[0] = row[2];
+                    if (right) row[C::TW - 1] = row[C::TW - 3];
+                }
+                __syncthreads();
             }
-            __syncthreads();
-        }
-        if (top || bottom) {
-            for (int i = tid; i < C::CIN * C::TW; i += C::THREADS) {
-                int c = i / C::TW, qq = i % C::TW;
-                __nv_bfloat16* ch = rawX + (size_t)c * C::TH * C::TWB + C::XOFF + qq;
-                if (top) ch[0] = ch[2 * C::TWB];
-                if (bottom) ch[(C::TH - 1) * C::TWB] = ch[(C::TH - 3) * C::TWB];
+            if (top || bottom) {
+                for (int i = tid; i < C::CIN * C::TW; i += C::THREADS) {
+                    int c = i / C::TW, qq = i % C::TW;
+                    __nv_bfloat16* ch = rawX + (size_t)c * C::TH * C::TWB + C::XOFF + qq;
+                    if (top) ch[0] = ch[2 * C::TWB];
+                    if (bottom) ch[(C::TH - 1) * C::TWB] = ch[(C::TH - 3) * C::TWB];
+                }
             }
-        }
-        if (!p.w_bulk || top || bottom) __syncthreads();
+        };
+        if (!p.w_bulk) __syncthreads();
+        HSB_STAMP(1);
 
         // ---------------- P1: re-stage into UMMA operand layouts ----------------
-        {   // x tile -> A1 (K-major): unit(m, kc) = kc*LBO + (m/8)*SBO + (m%8)*16 bytes = 8 channels of pixel m.
+        auto restage_x = [&]() {
+            // x tile -> A1 (K-major): unit(m, kc) = kc*LBO + (m/8)*SBO + (m%8)*16 bytes = 8 channels of pixel m.
             // Lanes walk consecutive pixels: 2-byte reads of one tile row are contiguous, the 16-byte writes of a warp
             // cover 512 contiguous bytes -> no bank conflicts either way.  Channel CIN is the constant one; k-chunks
             // past it keep whatever finite bytes A2 left there (their B1 columns are zero).
@@ -252,6 +278,8 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                 *reinterpret_cast<uint4*>(sm + C::OFF_A1 + kc * C::A1_LBO + (m >> 3) * C::A1_SBO + (m & 7) * 16) =
                     make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
             }
+        };
+        {
             // W1 -> B1 (K-major): unit(n, kc) = kc*LBO + (n/8)*SBO + (n%8)*16; row n = s1[n]*W1[n][:], b1[n] at k=CIN.
             // Every unit of B1 is rewritten (zeros for padding rows / columns): the region is shared with A2.
             for (int i = tid; i < C::N1 * (C::K1 / 8); i += C::THREADS) {
@@ -307,13 +335,19 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                 w2p[tap * C::HPW + cp] = pack_bf16(lo, hi);
             }
         }
+        // the x tile is only needed now: its flight time hid behind the weight re-stage
+        if (p.w_bulk) mbar_wait(bar_tma, par);
+        patch_halo();
+        if (top || bottom) __syncthreads();
+        restage_x();
         fence_proxy_async_smem();          // operand writes -> visible to the tensor core (async proxy)
         tc_fence_before_sync();
         __syncthreads();
+        HSB_STAMP(2);
 
         // ---------------- P2: GEMM1; the next patch's weight row starts to stream in ----------------
         const int next = patch + gridDim.x;
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after_sync();
             for (int t = 0; t < C::M1T; ++t) {
 #pragma unroll
@@ -324,14 +358,18 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                 }
                 umma_commit(bar_mma1 + t);
             }
-            if (next < p.total) announce_and_load_w(next, par ^ 1);     // rawW was consumed in P1
         }
+        if (warp == 1 && elect_one() && next < p.total) announce_and_load_w(next, par ^ 1);     // rawW was consumed in P1
 
         // ---------------- P3: epilogue 1 (TMEM -> ReLU6 -> hidden tile, which overwrites the raw x tile) ----------------
-        for (int t = 0; t < C::M1T; ++t) mbar_wait(bar_mma1 + t, par);      // every tile done: A1/B1 are dead (P4 overwrites them)
-        tc_fence_after_sync();
+        HSB_STAMP(3);
+        HSB_STAMP(4);
         for (int t = q_rank; t < C::M1T; t += q_warps) {
             if (t * 128 + q * 32 >= C::T) continue;             // warp-uniform: no real pixels in this quadrant
+            // quadrant 0 of every tile holds real pixels, so each tile is waited for by some warp before the barrier
+            // below: all of GEMM1 is complete (A1/B1 dead) when P4 starts overwriting region Y
+            mbar_wait(bar_mma1 + t, par);
+            tc_fence_after_sync();
             const int m = t * 128 + q * 32 + lane;
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + t * C::N1;
             unsigned char* hrow = sm + C::OFF_HID + (size_t)m * (C::HPITCH * 2);
@@ -380,6 +418,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         }
         tc_fence_before_sync();
         __syncthreads();
+        HSB_STAMP(5);
 
         // ---------------- P4: depthwise 3x3 + BN2 + ReLU6 -> A2 (which overwrites A1/B1) ----------------
         {
@@ -496,10 +535,12 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
+        HSB_STAMP(6);
 
         // ---------------- P5: GEMM2 (accumulators reuse GEMM1's TMEM columns) ----------------
-        if (tid == 0) {
-            if (next < p.total) load_x(par ^ 1);        // region X is free: the depthwise phase has consumed the hidden tile
+        // region X is free: the depthwise phase has consumed the hidden tile
+        if (warp == 1 && elect_one() && next < p.total) load_x(par ^ 1);
+        if (warp == 0 && elect_one()) {
             tc_fence_after_sync();
             for (int t = 0; t < C::M2T; ++t) {
 #pragma unroll
@@ -514,6 +555,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
             }
         }
 
+        HSB_STAMP(7);
         // ---------------- P6: epilogue 2 (TMEM -> bf16 -> NCHW) ----------------
         for (int t = q_rank; t < C::M2T; t += q_warps) {
             mbar_wait(bar_mma2 + t, par);
@@ -536,7 +578,14 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         tc_fence_before_sync();
         __syncthreads();       // TMEM and the operand buffers are reused by the next patch
         tc_fence_after_sync();
+        HSB_STAMP(8);
     }
+#ifdef HSB_IR_PROF
+    if (tid == 0) {
+        for (int k = 0; k < 10; ++k) p.prof[(size_t)blockIdx.x * 12 + k] = prof_acc[k];
+        p.prof[(size_t)blockIdx.x * 12 + 10] = it;
+    }
+#endif
 
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
@@ -591,6 +640,28 @@ static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
         cudaGetLastError();
     }
     const int grid = std::min(p.total, std::max(1, device_sm_count()) * ctas);
+#ifdef HSB_IR_PROF
+    {   // profiling build: per-phase cycle sums of thread 0 of every CTA, printed after a synchronising launch
+        static long long* dprof = nullptr;
+        if (!dprof) cudaMalloc(&dprof, 4096 * 12 * sizeof(long long));
+        cudaMemsetAsync(dprof, 0, 4096 * 12 * sizeof(long long), st);
+        IRTCParams pp = p;
+        pp.prof = dprof;
+        kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, pp);
+        cudaStreamSynchronize(st);
+        static long long host[4096 * 12];
+        cudaMemcpy(host, dprof, sizeof(long long) * grid * 12, cudaMemcpyDeviceToHost);
+        double sum[10] = {0}; double patches = 0;
+        for (int g = 0; g < grid; ++g) { for (int k = 0; k < 10; ++k) sum[k] += (double)host[g * 12 + k]; patches += (double)host[g * 12 + 10]; }
+        static const char* names[10] = {"P0 wait loads", "P0 halo patch", "P1 restage", "P2 issue GEMM1", "P3 wait GEMM1", "P3 epilogue1",
+                                        "P4 depthwise", "P5 issue GEMM2", "P6 epilogue2", "loop top"};
+        double tot = 0; for (int k = 0; k < 10; ++k) tot += sum[k];
+        fprintf(stderr, "[hsb-prof] patch_ir_tc<%d,%d,%d,%d> grid %d, %.0f patches, %.0f cycles/patch (thread 0)\n", C::CIN, C::HID, C::COUT, C::PH,
+                grid, patches, tot / patches);
+        for (int k = 0; k < 10; ++k) fprintf(stderr, "[hsb-prof]   %-16s %8.0f cycles/patch  %5.1f %%\n", names[k], sum[k] / patches, 100.0 * sum[k] / tot);
+        return check_launch("patch_ir_tc launch");
+    }
+#endif
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
     return check_launch("patch_ir_tc launch");
 }

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                 fence_proxy_async_smem();
             }
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(b_full + st, (uint32_t)b_bytes);
                 bulk_g2s(b_sm + st * b_bytes, p.packed + ((size_t)g * p.otiles + t) * HD_NT * kpad, (uint32_t)b_bytes,
                          b_full + st);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
         for (int j = 0; j < nitems; ++j) {
             const int st = j & 1;
             if (j + 1 < nitems) stage_operands(j + 1);          // overlaps the MMAs / epilogue of item j
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_wait(b_full + st, (j >> 1) & 1);
                 if (j >= 2) mbar_wait(d_empty + st, ((j >> 1) - 1) & 1);      // epilogue drained this accumulator
                 tc_fence_after_sync();

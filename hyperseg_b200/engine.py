@@ -22,29 +22,38 @@ import torch.nn as nn
 from . import ops
 
 
-def _fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> None:
+def _fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d, keep_shift: bool = False):
+    """Scale of the eval-mode BatchNorm into the convolution's weights; its shift into the convolution's bias or,
+    with ``keep_shift``, returned so that it can be applied together with the activation that follows."""
     scale, shift = ops.fold_bn(bn)
     w = conv.weight.detach().float() * scale.view(-1, 1, 1, 1).to(conv.weight.device)
     b = shift.to(conv.weight.device)
     if conv.bias is not None:
         b = b + conv.bias.detach().float() * scale.to(conv.weight.device)
     conv.weight = nn.Parameter(w.to(conv.weight.dtype), requires_grad=False)
+    if keep_shift:
+        conv.bias = None
+        return b
     conv.bias = nn.Parameter(b.to(conv.weight.dtype), requires_grad=False)
+    return None
 
 
-def fold_static_batchnorms(model: nn.Module) -> int:
+def fold_static_batchnorms(model: nn.Module, fused_epilogues: bool = True) -> int:
     """Fold eval-mode BatchNorm2d into the static convolution that feeds it, in the encoder and the weight mapper.
 
-    The decoder's BatchNorms belong to the dynamic layers and are fused inside the CUDA kernels instead."""
-    from .nn.efficientnet import EfficientNet, MBConvBlock
+    In the encoder's MBConv blocks / stem / head the shift is kept apart (``FoldedBatchNorm``) so that shift, swish,
+    squeeze-and-excitation mean and skip add run as one channels-last pass (hsb_bias_act_nhwc_fwd) instead of
+    cuDNN's separate bias kernel plus three or four elementwise kernels.  The decoder's BatchNorms belong to the
+    dynamic layers and are fused inside the CUDA kernels instead."""
+    from .nn.efficientnet import EfficientNet, FoldedBatchNorm, MBConvBlock
     folded = 0
 
-    def fold(owner, conv_name, bn_name):
+    def fold(owner, conv_name, bn_name, keep_shift=False):
         nonlocal folded
         conv, bn = getattr(owner, conv_name, None), getattr(owner, bn_name, None)
         if isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d) and not bn.training:
-            _fold_conv_bn(conv, bn)
-            setattr(owner, bn_name, nn.Identity())
+            shift = _fold_conv_bn(conv, bn, keep_shift)
+            setattr(owner, bn_name, FoldedBatchNorm(shift) if keep_shift else nn.Identity())
             folded += 1
 
     for root_name in ("backbone", "weight_mapper"):
@@ -53,12 +62,12 @@ def fold_static_batchnorms(model: nn.Module) -> int:
             continue
         for m in root.modules():
             if isinstance(m, EfficientNet):
-                fold(m, "_conv_stem", "_bn0")
-                fold(m, "_conv_head", "_bn1")
+                fold(m, "_conv_stem", "_bn0", fused_epilogues)
+                fold(m, "_conv_head", "_bn1", fused_epilogues)
             elif isinstance(m, MBConvBlock):
-                fold(m, "_expand_conv", "_bn0")
-                fold(m, "_depthwise_conv", "_bn1")
-                fold(m, "_project_conv", "_bn2")
+                fold(m, "_expand_conv", "_bn0", fused_epilogues)
+                fold(m, "_depthwise_conv", "_bn1", fused_epilogues)
+                fold(m, "_project_conv", "_bn2", fused_epilogues)
             elif isinstance(m, nn.Sequential):
                 names = [n for n, _ in m.named_children()]
                 for a, b in zip(names, names[1:]):
@@ -92,6 +101,11 @@ class SegmentationEngine:
         for m, (scale, shift) in pinned:
             m._hsb_folded = (scale.to(self.device, torch.float32).contiguous(),
                              shift.to(self.device, torch.float32).contiguous())
+        if channels_last:           # the encoder epilogue kernels walk channels-last rows
+            from .nn.efficientnet import FoldedBatchNorm
+            for m in self.net.modules():
+                if isinstance(m, FoldedBatchNorm):
+                    m.shift32 = m.shift_master.to(self.device, torch.float32).contiguous()
         self.stream = torch.cuda.Stream(self.device)
         self.frames_dev = torch.zeros(self.shape, device=self.device, dtype=torch.float32)
         self.host_out = torch.empty((batch, height, width), dtype=torch.uint8).pin_memory()

@@ -18,6 +18,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
+
 # (repeats, kernel, stride, expand, in, out, se_ratio) of the EfficientNet-B0 stages
 _B0_STAGES = (
     (1, 3, 1, 1, 32, 16, 0.25),
@@ -112,19 +114,54 @@ class MBConvBlock(nn.Module):
     def forward(self, x, drop_connect_rate=None):
         y = x
         if self.expand:
-            y = F.silu(self._bn0(self._expand_conv(y)))
-        y = F.silu(self._bn1(self._depthwise_conv(y)))
+            y = _norm_act(self._bn0, self._expand_conv(y), True)
         if self.has_se:
-            gate = self._se_expand(F.silu(self._se_reduce(F.adaptive_avg_pool2d(y, 1))))
-            y = torch.sigmoid(gate) * y
-        y = self._bn2(self._project_conv(y))
-        if self.skip:
-            if drop_connect_rate and self.training:
-                keep = 1 - drop_connect_rate
-                mask = torch.floor(keep + _uniform_per_sample(y))
-                y = y / keep * mask
-            y = y + x
-        return y
+            y, squeezed = _norm_act(self._bn1, self._depthwise_conv(y), True, pool=True)
+            gate = self._se_expand(F.silu(self._se_reduce(squeezed)))
+            if getattr(self._bn1, "shift32", None) is not None and ops.nhwc_epilogue_ok(y):
+                y = ops.channel_gate_nhwc_(y, gate)
+            else:
+                y = torch.sigmoid(gate) * y
+        else:
+            y = _norm_act(self._bn1, self._depthwise_conv(y), True)
+        y = self._project_conv(y)
+        if self.skip and drop_connect_rate and self.training:
+            y = self._bn2(y)
+            keep = 1 - drop_connect_rate
+            mask = torch.floor(keep + _uniform_per_sample(y))
+            return y / keep * mask + x
+        return _norm_act(self._bn2, y, False, residual=x if self.skip else None)
+
+
+class FoldedBatchNorm(nn.Module):
+    """What an inference engine leaves in a BatchNorm's slot after folding the scale into the convolution before
+    it: the per-channel shift.  ``shift32`` (set by the engine once the module sits on its device) switches
+    :func:`_norm_act` to the one-pass channels-last epilogue kernel."""
+
+    def __init__(self, shift):
+        super().__init__()
+        self.register_buffer("shift", shift.detach().clone())
+        self.shift_master = shift.detach().float().clone()      # survives .to(dtype=bfloat16)
+        self.shift32 = None
+
+    def forward(self, y):
+        return y + self.shift.to(y.dtype).view(1, -1, 1, 1)
+
+
+def _norm_act(bn, y, swish, residual=None, pool=False):
+    """BatchNorm (or its folded remainder) -> optional swish -> optional skip add [-> squeeze for SE]: the
+    reference's efficientnet.py:97-98, :101-102, :106, :113, :122 -- one kernel on the engine path."""
+    shift = getattr(bn, "shift32", None)
+    if shift is not None and ops.nhwc_epilogue_ok(y) and (residual is None or ops.nhwc_epilogue_ok(residual)):
+        return ops.bias_act_nhwc_(y, shift, "silu" if swish else "none", residual, pool)
+    y = bn(y)
+    if swish:
+        y = F.silu(y)
+    if residual is not None:
+        y = y + residual
+    if pool:
+        return y, F.adaptive_avg_pool2d(y, 1)
+    return y
 
 
 def _uniform_per_sample(y):
@@ -192,7 +229,7 @@ class EfficientNet(nn.Module):
         self._fc = head(head_out, num_classes) if head is not None else None
 
     def _trunk(self, x, collect):
-        x = F.silu(self._bn0(self._conv_stem(x)))
+        x = _norm_act(self._bn0, self._conv_stem(x), True)
         feats = []
         n = len(self._blocks)
         for i, block in enumerate(self._blocks):
@@ -201,7 +238,7 @@ class EfficientNet(nn.Module):
             if collect and self._tap[i]:
                 fc = getattr(self, f'_feat_fc_{len(feats)}', None) if self.out_feat_scale is not None else None
                 feats.append(x if fc is None else fc(x))
-        x = F.silu(self._bn1(self._conv_head(x)))
+        x = _norm_act(self._bn1, self._conv_head(x), True)
         return x, feats
 
     def forward(self, x):

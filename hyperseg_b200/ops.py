@@ -14,7 +14,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, HSB_BF16, HSB_F32, PAD_MODES, W_NCHW, W_PATCH_MAJOR
+from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SILU, HSB_BF16, HSB_F32, PAD_MODES, W_NCHW, W_PATCH_MAJOR
 
 import os
 
@@ -32,7 +32,7 @@ def _call(fn_name, *args):
     _LAUNCHES += 1
 
 
-ACTS = {"none": ACT_NONE, None: ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6}
+ACTS = {"none": ACT_NONE, None: ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6, "silu": ACT_SILU}
 _DTYPES = {torch.float32: HSB_F32, torch.bfloat16: HSB_BF16}
 
 
@@ -359,6 +359,48 @@ def upsample_argmax(logits, size):
     labels = torch.empty((B, H, W), dtype=torch.uint8, device=logits.device)
     _call("hsb_upsample_argmax_fwd", logits.data_ptr(), labels.data_ptr(), B, C, h, w, H, W, _DTYPES[dt], _stream())
     return labels
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# encoder epilogues (engine path): channels-last activations of the static encoder, BatchNorm already folded
+# ---------------------------------------------------------------------------------------------------------------------
+def nhwc_epilogue_ok(x: torch.Tensor) -> bool:
+    """True when ``x`` is a CUDA (N, C, H, W) tensor stored channels-last whose rows the 16-byte kernels can walk."""
+    return (x.is_cuda and x.dim() == 4 and x.dtype in _DTYPES and not _needs_grad(x)
+            and (x.shape[1] * x.element_size()) % 16 == 0 and x.shape[1] * x.element_size() <= 16 * 1024
+            and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0)
+
+
+def bias_act_nhwc_(x, bias, act="none", residual=None, pool=False):
+    """In place: x <- act(x + bias[c]) (+ residual) on a channels-last tensor; with ``pool`` also returns the mean
+    over H, W of the result as (N, C, 1, 1) (the squeeze of squeeze-and-excitation), summed in a fixed order."""
+    if not nhwc_epilogue_ok(x):
+        raise ValueError("bias_act_nhwc_ needs a channels-last CUDA tensor with 16-byte channel rows")
+    N, C, H, W = x.shape
+    if residual is not None and not (nhwc_epilogue_ok(residual) and residual.shape == x.shape and residual.dtype == x.dtype):
+        raise ValueError("residual must match x (shape, dtype, channels-last)")
+    if bias is not None and not (bias.dtype == torch.float32 and bias.numel() == C and bias.is_contiguous()):
+        raise ValueError("bias must be a contiguous float32 vector of C elements")
+    partial = None
+    if pool:
+        chunks = _lib.load().hsb_bias_act_nhwc_chunks(C, H * W, _DTYPES[x.dtype])
+        partial = torch.empty((N, chunks, C), dtype=torch.float32, device=x.device)
+    _call("hsb_bias_act_nhwc_fwd", x.data_ptr(), _fptr(bias), _fptr(residual), x.data_ptr(), _fptr(partial),
+          N, H * W, C, ACTS[act], _DTYPES[x.dtype], _stream())
+    if not pool:
+        return x
+    mean = partial.sum(dim=1).mul_(1.0 / (H * W)).to(x.dtype)
+    return x, mean.view(N, C, 1, 1)
+
+
+def channel_gate_nhwc_(x, gate):
+    """In place: x <- x * sigmoid(gate[n, c]); ``gate`` is (N, C, 1, 1) (the excitation of squeeze-and-excitation)."""
+    if not nhwc_epilogue_ok(x):
+        raise ValueError("channel_gate_nhwc_ needs a channels-last CUDA tensor with 16-byte channel rows")
+    N, C, H, W = x.shape
+    gate = gate.reshape(N, C).to(x.dtype).contiguous()
+    _call("hsb_channel_gate_nhwc_fwd", x.data_ptr(), gate.data_ptr(), x.data_ptr(), N, H * W, C, _DTYPES[x.dtype], _stream())
+    return x
 
 
 # ---------------------------------------------------------------------------------------------------------------------

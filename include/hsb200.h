@@ -47,7 +47,8 @@ typedef enum hsb_status {
 } hsb_status;
 
 typedef enum hsb_dtype { HSB_F32 = 0, HSB_BF16 = 1 } hsb_dtype;
-typedef enum hsb_act { HSB_ACT_NONE = 0, HSB_ACT_RELU = 1, HSB_ACT_RELU6 = 2 } hsb_act;
+typedef enum hsb_act { HSB_ACT_NONE = 0, HSB_ACT_RELU = 1, HSB_ACT_RELU6 = 2,
+                       HSB_ACT_SILU = 3 /* encoder epilogues only */ } hsb_act;
 typedef enum hsb_wlayout { HSB_W_NCHW = 0, HSB_W_PATCH_MAJOR = 1 } hsb_wlayout;
 typedef enum hsb_padmode { HSB_PAD_ZEROS = 0, HSB_PAD_REFLECT = 1, HSB_PAD_REPLICATE = 2,
                            HSB_PAD_CIRCULAR = 3 } hsb_padmode;
@@ -210,6 +211,24 @@ int hsb_upsample_argmax_fwd(const void* logits, void* labels, int B, int C, int 
  */
 int hsb_weights_to_patch_major(const void* w_nchw, void* w_pm, int B, int hp, int fh, int fw,
                                int64_t row_stride, int dtype, void* stream);
+
+/*
+ * Encoder epilogues (engine path, outside the decoder hot path): channels-last (N, HW, C) activations of the stock
+ * EfficientNet encoder after its eval-mode BatchNorms have been folded into the convolutions
+ * (hyperseg/models/backbones/efficientnet.py:82-123 MBConvBlock.forward, :275 stem, :289 head).
+ *   hsb_bias_act_nhwc_fwd      y = act(x + bias[c]) (+ residual); y may alias x.  Replaces BatchNorm + swish (:97-98,
+ *                              :101-102, :275, :289), BatchNorm after the projection and the skip add (:113, :122).
+ *                              With pool_partial != NULL also writes per-chunk sums of the rounded output,
+ *                              (N, chunks, C) float32 with chunks = hsb_bias_act_nhwc_chunks(C, HW, dtype); their sum
+ *                              over chunks / HW is F.adaptive_avg_pool2d(y, 1) (:106), in a fixed summation order.
+ *   hsb_channel_gate_nhwc_fwd  y = x * sigmoid(gate[n, c])  (:110); gate is (N, C) of the same dtype.
+ * C * sizeof(element) must be a multiple of 16, tensors 16-byte aligned.
+ */
+int hsb_bias_act_nhwc_chunks(int C, int64_t HW, int dtype);
+int hsb_bias_act_nhwc_fwd(const void* x, const float* bias, const void* residual, void* y, float* pool_partial,
+                          int N, int64_t HW, int C, int act, int dtype, void* stream);
+int hsb_channel_gate_nhwc_fwd(const void* x, const void* gate, void* y, int N, int64_t HW, int C, int dtype,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python scripts/train_debug.py > gpurun_out/train_debug.log 2>&1
-timeout 600 python -m pytest tests/test_grads.py -m gpu -q 2>&1 | tail -15
+export HSB_VERBOSE=0
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_n1.log 2>&1; tail -1 gpurun_out/bench_n1.log | cut -c1-1500

@@ -342,3 +342,79 @@ def test_engine_labels_match_model_argmax():
         agree = (labels.long() == ref).float().mean().item()
         assert agree > 0.97, agree                        # bf16 engine vs autocast reference path
         assert eng.launches_per_step >= 16                # 5 heads + 5 patch kernels + 5 glue + tail, all ours
+
+
+# ---- encoder epilogues (engine path) ---------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("geom", [(2, 96, 64, 128), (1, 16, 33, 20), (3, 1152, 4, 8), (2, 40, 1, 1), (1, 8, 7, 300)])
+@pytest.mark.parametrize("act", ["silu", "none"])
+def test_bias_act_nhwc_matches_torch(geom, dtype, act):
+    """y = act(x + shift) (+ skip) and the squeeze-and-excitation mean, against the stock elementwise sequence
+    (reference efficientnet.py:97-122 with the BatchNorm folded)."""
+    from hyperseg_b200 import ops
+    N, C, H, W = geom
+    g = torch.Generator().manual_seed(C * 131 + H)
+    x = (torch.randn(N, C, H, W, generator=g) * 2).to("cuda", dtype).contiguous(memory_format=torch.channels_last)
+    res = torch.randn(N, C, H, W, generator=g).to("cuda", dtype).contiguous(memory_format=torch.channels_last)
+    shift = torch.randn(C, generator=g).cuda()
+    ref = x.float() + shift.view(1, -1, 1, 1)
+    ref = torch.nn.functional.silu(ref) if act == "silu" else ref
+    tol = 1e-6 if dtype == torch.float32 else 8e-3
+    y, mean = ops.bias_act_nhwc_(x.clone(memory_format=torch.channels_last), shift, act, None, pool=True)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert (y.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+    assert mean.shape == (N, C, 1, 1)
+    assert (mean.float() - y.float().mean((2, 3), keepdim=True)).abs().max().item() <= tol * max(1.0, mean.float().abs().max().item())
+    y2 = ops.bias_act_nhwc_(x.clone(memory_format=torch.channels_last), shift, act, res)
+    assert (y2.float() - (ref + res.float())).abs().max().item() <= tol * max(1.0, ref.abs().max().item() + 4)
+    # deterministic (fixed summation order)
+    _, mean2 = ops.bias_act_nhwc_(x.clone(memory_format=torch.channels_last), shift, act, None, pool=True)
+    assert torch.equal(mean, mean2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("geom", [(2, 96, 64, 128), (1, 16, 33, 20), (3, 1152, 4, 8)])
+def test_channel_gate_nhwc_matches_torch(geom, dtype):
+    from hyperseg_b200 import ops
+    N, C, H, W = geom
+    g = torch.Generator().manual_seed(C + 7)
+    x = torch.randn(N, C, H, W, generator=g).to("cuda", dtype).contiguous(memory_format=torch.channels_last)
+    gate = (torch.randn(N, C, 1, 1, generator=g) * 3).to("cuda", dtype)
+    ref = torch.sigmoid(gate) * x
+    y = ops.channel_gate_nhwc_(x.clone(memory_format=torch.channels_last), gate)
+    tol = 1e-6 if dtype == torch.float32 else 8e-3
+    assert (y.float() - ref.float()).abs().max().item() <= tol * max(1.0, ref.float().abs().max().item())
+
+
+@pytest.mark.gpu
+def test_encoder_epilogues_refuse_other_layouts():
+    from hyperseg_b200 import ops
+    x = torch.zeros(1, 16, 4, 4, device="cuda")                       # NCHW-contiguous
+    with pytest.raises(ValueError):
+        ops.bias_act_nhwc_(x, torch.zeros(16, device="cuda"), "silu")
+    x = torch.zeros(1, 3, 4, 4, device="cuda").contiguous(memory_format=torch.channels_last)   # 12-byte rows
+    with pytest.raises(ValueError):
+        ops.channel_gate_nhwc_(x, torch.zeros(1, 3, 1, 1, device="cuda"))
+
+
+@pytest.mark.gpu
+def test_engine_fused_encoder_epilogues_match_stock_encoder():
+    """The engine with the one-pass encoder epilogues against the same engine on stock elementwise kernels."""
+    from hyperseg_b200.engine import SegmentationEngine, fold_static_batchnorms
+    from hyperseg_b200.nn.efficientnet import FoldedBatchNorm
+    from hyperseg_b200.synthetic import build_model, synthetic_frames
+    model = build_model("hyperseg-m", seed=0).eval()
+    frames = synthetic_frames(2, 128, 256).pin_memory()
+    eng = SegmentationEngine(model, batch=2, height=128, width=256, use_graph=False)
+    assert any(isinstance(m, FoldedBatchNorm) and m.shift32 is not None for m in eng.net.modules())
+    labels = eng(frames).clone()
+    logits = eng.full_logits().float()
+    for m in eng.net.modules():                      # same engine, stock path: y + shift, silu, mean, sigmoid * y
+        if isinstance(m, FoldedBatchNorm):
+            m.shift32 = None
+    labels_stock = eng(frames).clone()
+    logits_stock = eng.full_logits().float()
+    assert (logits - logits_stock).abs().max().item() < 3e-2 * logits_stock.abs().max().item()
+    assert (labels == labels_stock).float().mean().item() > 0.97
