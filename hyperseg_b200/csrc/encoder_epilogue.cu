@@ -122,12 +122,16 @@ __global__ void channel_gate_nhwc_kernel(const GateParams p) {
     }
 }
 
+constexpr int MAX_CHUNKS = 64;
+
 // thread arrangement shared by both kernels: G = C/N channel groups x L row lanes, <= 256 threads
 static void arrange(int C, int vec, int HW, int& G, int& L, int& rows_per_cta, int& chunks) {
     G = C / vec;
     L = G >= 256 ? 1 : 256 / G;
     if (L > HW) L = HW;
     rows_per_cta = L * 16;
+    const int cap = (HW + MAX_CHUNKS - 1) / MAX_CHUNKS;          // at most MAX_CHUNKS partial sums per image
+    if (rows_per_cta < cap) rows_per_cta = (cap + L - 1) / L * L;
     chunks = (HW + rows_per_cta - 1) / rows_per_cta;
 }
 

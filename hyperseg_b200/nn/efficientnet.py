@@ -117,11 +117,11 @@ class MBConvBlock(nn.Module):
             y = _norm_act(self._bn0, self._expand_conv(y), True)
         if self.has_se:
             y, squeezed = _norm_act(self._bn1, self._depthwise_conv(y), True, pool=True)
+            fused = squeezed.dim() == 3         # engine path: per-chunk sums from the epilogue kernel (N, chunks, C)
+            if fused:
+                squeezed = ops.pooled_mean(squeezed, y.shape[2] * y.shape[3], y.dtype)
             gate = self._se_expand(F.silu(self._se_reduce(squeezed)))
-            if getattr(self._bn1, "shift32", None) is not None and ops.nhwc_epilogue_ok(y):
-                y = ops.channel_gate_nhwc_(y, gate)
-            else:
-                y = torch.sigmoid(gate) * y
+            y = ops.channel_gate_nhwc_(y, gate) if fused else torch.sigmoid(gate) * y
         else:
             y = _norm_act(self._bn1, self._depthwise_conv(y), True)
         y = self._project_conv(y)

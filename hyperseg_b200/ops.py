@@ -372,8 +372,9 @@ def nhwc_epilogue_ok(x: torch.Tensor) -> bool:
 
 
 def bias_act_nhwc_(x, bias, act="none", residual=None, pool=False):
-    """In place: x <- act(x + bias[c]) (+ residual) on a channels-last tensor; with ``pool`` also returns the mean
-    over H, W of the result as (N, C, 1, 1) (the squeeze of squeeze-and-excitation), summed in a fixed order."""
+    """In place: x <- act(x + bias[c]) (+ residual) on a channels-last tensor; with ``pool`` also returns per-chunk
+    sums of the result, (N, chunks, C) float32 -- the squeeze of squeeze-and-excitation before its division by H*W,
+    in a fixed summation order (see :func:`pooled_mean`)."""
     if not nhwc_epilogue_ok(x):
         raise ValueError("bias_act_nhwc_ needs a channels-last CUDA tensor with 16-byte channel rows")
     N, C, H, W = x.shape
@@ -384,13 +385,18 @@ def bias_act_nhwc_(x, bias, act="none", residual=None, pool=False):
     partial = None
     if pool:
         chunks = _lib.load().hsb_bias_act_nhwc_chunks(C, H * W, _DTYPES[x.dtype])
+        if chunks <= 0:
+            raise ValueError("bad geometry for the pooled epilogue")
         partial = torch.empty((N, chunks, C), dtype=torch.float32, device=x.device)
     _call("hsb_bias_act_nhwc_fwd", x.data_ptr(), _fptr(bias), _fptr(residual), x.data_ptr(), _fptr(partial),
           N, H * W, C, ACTS[act], _DTYPES[x.dtype], _stream())
-    if not pool:
-        return x
-    mean = partial.sum(dim=1).mul_(1.0 / (H * W)).to(x.dtype)
-    return x, mean.view(N, C, 1, 1)
+    return (x, partial) if pool else x
+
+
+def pooled_mean(partial, hw, dtype):
+    """(N, chunks, C) partial sums -> F.adaptive_avg_pool2d result (N, C, 1, 1)."""
+    N, _, C = partial.shape
+    return partial.sum(dim=1).mul_(1.0 / hw).to(dtype).view(N, C, 1, 1)
 
 
 def channel_gate_nhwc_(x, gate):

@@ -361,7 +361,9 @@ def test_bias_act_nhwc_matches_torch(geom, dtype, act):
     ref = x.float() + shift.view(1, -1, 1, 1)
     ref = torch.nn.functional.silu(ref) if act == "silu" else ref
     tol = 1e-6 if dtype == torch.float32 else 8e-3
-    y, mean = ops.bias_act_nhwc_(x.clone(memory_format=torch.channels_last), shift, act, None, pool=True)
+    y, partial = ops.bias_act_nhwc_(x.clone(memory_format=torch.channels_last), shift, act, None, pool=True)
+    assert partial.shape[0] == N and partial.shape[2] == C and partial.shape[1] <= 64
+    mean = ops.pooled_mean(partial, H * W, dtype)
     assert y.is_contiguous(memory_format=torch.channels_last)
     assert (y.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
     assert mean.shape == (N, C, 1, 1)
@@ -369,8 +371,8 @@ def test_bias_act_nhwc_matches_torch(geom, dtype, act):
     y2 = ops.bias_act_nhwc_(x.clone(memory_format=torch.channels_last), shift, act, res)
     assert (y2.float() - (ref + res.float())).abs().max().item() <= tol * max(1.0, ref.abs().max().item() + 4)
     # deterministic (fixed summation order)
-    _, mean2 = ops.bias_act_nhwc_(x.clone(memory_format=torch.channels_last), shift, act, None, pool=True)
-    assert torch.equal(mean, mean2)
+    _, partial2 = ops.bias_act_nhwc_(x.clone(memory_format=torch.channels_last), shift, act, None, pool=True)
+    assert torch.equal(partial, partial2)
 
 
 @pytest.mark.gpu
