@@ -162,6 +162,53 @@ class SegmentationEngine:
         self.stream.synchronize()
         return self.host_out
 
+    # ---- pipelined host -> host stream: the upload of batch k+1 overlaps the forward of batch k -------------------------
+    def _pipeline(self):
+        if getattr(self, "_pipe", None) is None:
+            self._pipe = dict(
+                copy_stream=torch.cuda.Stream(self.device),
+                staging=[torch.empty(self.shape, device=self.device, dtype=torch.float32) for _ in range(2)],
+                host_out=[torch.empty(self.host_out.shape, dtype=torch.uint8).pin_memory() for _ in range(2)],
+                copied=[torch.cuda.Event() for _ in range(2)], consumed=[torch.cuda.Event() for _ in range(2)],
+                done=[torch.cuda.Event() for _ in range(2)], submitted=0, collected=0)
+        return self._pipe
+
+    @torch.no_grad()
+    def submit(self, frames: torch.Tensor) -> None:
+        """Enqueue one batch of host frames (pinned float32); at most two batches may be in flight.  The H2D copy runs
+        on its own stream into a staging buffer, so it overlaps the forward of the batch submitted before."""
+        if tuple(frames.shape) != self.shape:
+            raise ValueError(f"engine was built for frames of shape {self.shape}, got {tuple(frames.shape)}")
+        p = self._pipeline()
+        if p["submitted"] - p["collected"] >= 2:
+            raise RuntimeError("two batches are already in flight: collect() one first")
+        i = p["submitted"] % 2
+        with torch.cuda.stream(p["copy_stream"]):
+            p["copy_stream"].wait_event(p["consumed"][i])          # the forward two batches ago has read this buffer
+            p["staging"][i].copy_(frames, non_blocking=True)
+            p["copied"][i].record(p["copy_stream"])
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(p["copied"][i])
+            self.frames_dev.copy_(p["staging"][i], non_blocking=True)
+            p["consumed"][i].record(self.stream)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._forward_static()
+            p["host_out"][i].copy_(self.labels, non_blocking=True)
+            p["done"][i].record(self.stream)
+        p["submitted"] += 1
+
+    def collect(self) -> torch.Tensor:
+        """Host labels (pinned uint8, B x H x W) of the oldest batch in flight; valid until two more are submitted."""
+        p = self._pipeline()
+        if p["collected"] >= p["submitted"]:
+            raise RuntimeError("nothing in flight")
+        j = p["collected"] % 2
+        p["done"][j].synchronize()
+        p["collected"] += 1
+        return p["host_out"][j]
+
     @torch.no_grad()
     def full_logits(self) -> torch.Tensor:
         """Logits of the last step at frame resolution (what model(frames) returns), computed on demand."""

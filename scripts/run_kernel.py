@@ -32,6 +32,9 @@ elif which == "head4":
 elif which == "head0":
     s = rnd(B, 1280, 16, 32).abs(); ws = rnd(5248, 13, 1, 1, scale=0.2)
     fn = lambda: ops.signal2weights(s, ws, 0, 416, 5248, 32)
+elif which == "epi":
+    x = rnd(B, 96, 256, 512).contiguous(memory_format=torch.channels_last); sh = torch.randn(96, generator=g).to(dev)
+    fn = lambda: ops.bias_act_nhwc_(x, sh, "silu", None, pool=True)
 for _ in range(4):
     fn()
 torch.cuda.synchronize()

@@ -420,3 +420,29 @@ def test_engine_fused_encoder_epilogues_match_stock_encoder():
     logits_stock = eng.full_logits().float()
     assert (logits - logits_stock).abs().max().item() < 3e-2 * logits_stock.abs().max().item()
     assert (labels == labels_stock).float().mean().item() > 0.97
+
+
+@pytest.mark.gpu
+def test_engine_pipelined_stream_equals_blocking_calls():
+    """submit()/collect() (upload of batch k+1 overlapping the forward of batch k) returns, in order, exactly the label
+    maps of the blocking __call__ on the same batches."""
+    from hyperseg_b200.engine import SegmentationEngine
+    from hyperseg_b200.synthetic import build_model, synthetic_frames
+    model = build_model("hyperseg-m", seed=0).eval()
+    eng = SegmentationEngine(model, batch=2, height=128, width=256)
+    batches = [synthetic_frames(2, 128, 256, seed=40 + i).pin_memory() for i in range(5)]
+    want = [eng(b).clone() for b in batches]
+    assert not torch.equal(want[0], want[1])
+    got = []
+    for k, b in enumerate(batches):
+        eng.submit(b)
+        if k > 0:
+            got.append(eng.collect().clone())
+    got.append(eng.collect().clone())
+    assert len(got) == len(want) and all(torch.equal(g, w) for g, w in zip(got, want))
+    with pytest.raises(RuntimeError):
+        eng.collect()
+    eng.submit(batches[0]); eng.submit(batches[1])
+    with pytest.raises(RuntimeError):
+        eng.submit(batches[2])
+    assert torch.equal(eng.collect(), want[0]) and torch.equal(eng.collect(), want[1])
