@@ -12,6 +12,8 @@
 
 namespace hsb {
 
+constexpr int ROWS = 2;       // rows (16-byte loads) in flight per thread
+
 template <typename T> struct Vec16;
 template <> struct Vec16<float> { static constexpr int N = 4; };
 template <> struct Vec16<__nv_bfloat16> { static constexpr int N = 8; };
@@ -44,8 +46,12 @@ __device__ __forceinline__ uint4 pack16(float (&v)[N]) {
     }
 }
 
+// The pass is instruction-issue bound before it is HBM bound (ncu: 31 instructions per element with IEEE exp +
+// division), so swish uses the SFU approximations: ex2.approx + rcp.approx, relative error ~2e-7 -- far inside bf16.
+__device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
+
 __device__ __forceinline__ float epilogue_act(float v, int act) {
-    if (act == HSB_ACT_SILU) return v / (1.f + expf(-v));
+    if (act == HSB_ACT_SILU) return v * fast_sigmoid(v);
     return act_apply(v, act);
 }
 
@@ -54,7 +60,9 @@ struct BiasActParams {
     int HW, C, G, L, rows_per_cta, chunks, act;
 };
 
-template <typename T>
+// ACT: a compile-time hsb_act, or -1 for "read p.act" (the activations the encoder does not use); RES / POOL switch
+// the skip add and the partial sums: the inner loop carries no run-time mode tests
+template <typename T, int ACT, bool RES, bool POOL>
 __global__ void bias_act_nhwc_kernel(const BiasActParams p) {
     constexpr int N = Vec16<T>::N;
     extern __shared__ float red[];                       // [L][C] partial sums
@@ -62,28 +70,46 @@ __global__ void bias_act_nhwc_kernel(const BiasActParams p) {
     const int n = blockIdx.y, chunk = blockIdx.x;
     const size_t base = (size_t)n * p.HW * p.C + (size_t)g * N;
     const T* x = reinterpret_cast<const T*>(p.x) + base;
-    const T* res = p.res ? reinterpret_cast<const T*>(p.res) + base : nullptr;
+    const T* res = RES ? reinterpret_cast<const T*>(p.res) + base : nullptr;
     T* y = reinterpret_cast<T*>(p.y) + base;
     float b[N], acc[N];
 #pragma unroll
     for (int e = 0; e < N; ++e) { b[e] = p.bias ? p.bias[g * N + e] : 0.f; acc[e] = 0.f; }
     const int r_end = min(p.HW, (chunk + 1) * p.rows_per_cta);
-    for (int r = chunk * p.rows_per_cta + l; r < r_end; r += p.L) {
-        float v[N];
-        unpack16<T, N>(*reinterpret_cast<const uint4*>(x + (size_t)r * p.C), v);
+    // ROWS independent 16-byte loads in flight per thread: the pass is HBM-bound and latency decides the bandwidth
+    for (int r0 = chunk * p.rows_per_cta + l; r0 < r_end; r0 += ROWS * p.L) {
+        uint4 raw[ROWS], rraw[ROWS];
 #pragma unroll
-        for (int e = 0; e < N; ++e) v[e] = epilogue_act(v[e] + b[e], p.act);
-        if (res) {
-            float s[N];
-            unpack16<T, N>(*reinterpret_cast<const uint4*>(res + (size_t)r * p.C), s);
-#pragma unroll
-            for (int e = 0; e < N; ++e) v[e] += s[e];
+        for (int u = 0; u < ROWS; ++u) {
+            const int r = r0 + u * p.L;
+            if (r < r_end) {
+                raw[u] = *reinterpret_cast<const uint4*>(x + (size_t)r * p.C);
+                if (RES) rraw[u] = *reinterpret_cast<const uint4*>(res + (size_t)r * p.C);
+            }
         }
-        *reinterpret_cast<uint4*>(y + (size_t)r * p.C) = pack16<T, N>(v);
 #pragma unroll
-        for (int e = 0; e < N; ++e) acc[e] += v[e];
+        for (int u = 0; u < ROWS; ++u) {
+            const int r = r0 + u * p.L;
+            if (r < r_end) {
+                float v[N];
+                unpack16<T, N>(raw[u], v);
+#pragma unroll
+                for (int e = 0; e < N; ++e) v[e] = epilogue_act(v[e] + b[e], ACT >= 0 ? ACT : p.act);
+                if (RES) {
+                    float s[N];
+                    unpack16<T, N>(rraw[u], s);
+#pragma unroll
+                    for (int e = 0; e < N; ++e) v[e] += s[e];
+                }
+                *reinterpret_cast<uint4*>(y + (size_t)r * p.C) = pack16<T, N>(v);
+                if (POOL) {
+#pragma unroll
+                    for (int e = 0; e < N; ++e) acc[e] += v[e];
+                }
+            }
+        }
     }
-    if (p.pool) {
+    if (POOL) {
 #pragma unroll
         for (int e = 0; e < N; ++e) red[l * p.C + g * N + e] = acc[e];
         __syncthreads();
@@ -108,17 +134,26 @@ __global__ void channel_gate_nhwc_kernel(const GateParams p) {
     float s[N];
     unpack16<T, N>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.gate) + (size_t)n * p.C + (size_t)g * N), s);
 #pragma unroll
-    for (int e = 0; e < N; ++e) s[e] = 1.f / (1.f + expf(-s[e]));
+    for (int e = 0; e < N; ++e) s[e] = fast_sigmoid(s[e]);
     if constexpr (N == 8) {                               // torch rounds sigmoid(gate) to bf16 before the product
         (void)pack16<T, N>(s);
     }
     const int r_end = min(p.HW, (chunk + 1) * p.rows_per_cta);
-    for (int r = chunk * p.rows_per_cta + l; r < r_end; r += p.L) {
-        float v[N];
-        unpack16<T, N>(*reinterpret_cast<const uint4*>(x + (size_t)r * p.C), v);
+    for (int r0 = chunk * p.rows_per_cta + l; r0 < r_end; r0 += ROWS * p.L) {
+        uint4 raw[ROWS];
 #pragma unroll
-        for (int e = 0; e < N; ++e) v[e] *= s[e];
-        *reinterpret_cast<uint4*>(y + (size_t)r * p.C) = pack16<T, N>(v);
+        for (int u = 0; u < ROWS; ++u)
+            if (r0 + u * p.L < r_end) raw[u] = *reinterpret_cast<const uint4*>(x + (size_t)(r0 + u * p.L) * p.C);
+#pragma unroll
+        for (int u = 0; u < ROWS; ++u) {
+            if (r0 + u * p.L < r_end) {
+                float v[N];
+                unpack16<T, N>(raw[u], v);
+#pragma unroll
+                for (int e = 0; e < N; ++e) v[e] *= s[e];
+                *reinterpret_cast<uint4*>(y + (size_t)(r0 + u * p.L) * p.C) = pack16<T, N>(v);
+            }
+        }
     }
 }
 
@@ -164,8 +199,18 @@ extern "C" int hsb_bias_act_nhwc_fwd(const void* x, const float* bias, const voi
     const size_t smem = pool_partial ? (size_t)p.L * C * sizeof(float) : 0;
     HSB_REQUIRE(smem <= 48 * 1024, HSB_ERR_UNSUPPORTED, "bias_act_nhwc: channel count too large for the pooled variant");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (dtype == HSB_BF16) bias_act_nhwc_kernel<__nv_bfloat16><<<grid, block, smem, st>>>(p);
-    else bias_act_nhwc_kernel<float><<<grid, block, smem, st>>>(p);
+    const bool bf = dtype == HSB_BF16, has_res = residual != nullptr, has_pool = pool_partial != nullptr;
+#define HSB_EPI_LAUNCH(T, A)                                                                              \
+    do {                                                                                                  \
+        if (has_res && has_pool) bias_act_nhwc_kernel<T, A, true, true><<<grid, block, smem, st>>>(p);    \
+        else if (has_res) bias_act_nhwc_kernel<T, A, true, false><<<grid, block, smem, st>>>(p);          \
+        else if (has_pool) bias_act_nhwc_kernel<T, A, false, true><<<grid, block, smem, st>>>(p);         \
+        else bias_act_nhwc_kernel<T, A, false, false><<<grid, block, smem, st>>>(p);                      \
+    } while (0)
+    if (act == HSB_ACT_SILU) { if (bf) HSB_EPI_LAUNCH(__nv_bfloat16, HSB_ACT_SILU); else HSB_EPI_LAUNCH(float, HSB_ACT_SILU); }
+    else if (act == HSB_ACT_NONE) { if (bf) HSB_EPI_LAUNCH(__nv_bfloat16, HSB_ACT_NONE); else HSB_EPI_LAUNCH(float, HSB_ACT_NONE); }
+    else { if (bf) HSB_EPI_LAUNCH(__nv_bfloat16, -1); else HSB_EPI_LAUNCH(float, -1); }
+#undef HSB_EPI_LAUNCH
     return check_launch("bias_act_nhwc launch");
 }
 

@@ -129,9 +129,10 @@ class SegmentationEngine:
         self.stream.synchronize()
 
     def _forward_static(self):
-        x = self.frames_dev.to(self.dtype)
         net = self.net
-        xin = x.contiguous(memory_format=torch.channels_last) if self.channels_last else x
+        # one pass: fp32 NCHW frames -> compute dtype, channels-last (the decoder's glue kernel takes any strides)
+        x = self.frames_dev.to(self.dtype, memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+        xin = x
         feats = net.backbone(xin)                  # NHWC feature maps are consumed as they are by the glue kernel
         signal = net.weight_mapper(feats[-1]).contiguous()      # NCHW once: every head reads position-contiguous rows
         self.logits = net.decoder.forward_features([x] + feats[:-1], signal)      # at the last decoder level's size

@@ -360,7 +360,7 @@ def test_bias_act_nhwc_matches_torch(geom, dtype, act):
     shift = torch.randn(C, generator=g).cuda()
     ref = x.float() + shift.view(1, -1, 1, 1)
     ref = torch.nn.functional.silu(ref) if act == "silu" else ref
-    tol = 1e-6 if dtype == torch.float32 else 8e-3
+    tol = 2e-6 if dtype == torch.float32 else 8e-3        # fp32: SFU exp / reciprocal approximations (~2e-7 relative)
     y, partial = ops.bias_act_nhwc_(x.clone(memory_format=torch.channels_last), shift, act, None, pool=True)
     assert partial.shape[0] == N and partial.shape[2] == C and partial.shape[1] <= 64
     mean = ops.pooled_mean(partial, H * W, dtype)
@@ -386,7 +386,7 @@ def test_channel_gate_nhwc_matches_torch(geom, dtype):
     gate = (torch.randn(N, C, 1, 1, generator=g) * 3).to("cuda", dtype)
     ref = torch.sigmoid(gate) * x
     y = ops.channel_gate_nhwc_(x.clone(memory_format=torch.channels_last), gate)
-    tol = 1e-6 if dtype == torch.float32 else 8e-3
+    tol = 2e-6 if dtype == torch.float32 else 8e-3
     assert (y.float() - ref.float()).abs().max().item() <= tol * max(1.0, ref.float().abs().max().item())
 
 
