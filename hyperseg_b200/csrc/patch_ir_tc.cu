@@ -4,14 +4,17 @@
 //
 //   persistent CTAs, TWO (16x16) or THREE (8x8) resident per SM so that one CTA's barrier / tensor-core / TMA
 //   latencies are covered by another CTA's arithmetic; each CTA walks its patches:
-//   P0  wait for the TMA engine: the (ph+2)x(pw+2) halo tile of x arrives through a 4-D tensor map (box starting 8
-//       pixels left of the patch -- TMA wants a 16-byte aligned innermost start --, zero fill outside the image) and
-//       the patch's weight row through cp.async.bulk; image-border patches get their reflect halo patched in place;
-//   P1  re-stage: x tile -> UMMA operand A1 (K-major, lanes over pixels: conflict-free, with a constant-one channel
-//       that carries the BatchNorm shift), W1/W3 -> operands B1/B2 with the BatchNorm scale folded in and the shift
-//       as an extra K column, W2 -> packed bf16x2 taps; then the next patch's weight row is prefetched;
-//   P2  GEMM1 on the tensor core: H[(ph+2)(pw+2) px x hid] = A1 . B1^T, M=128 tiles accumulated in TMEM;
-//   P3  epilogue 1: TMEM -> registers -> ReLU6 -> bf16 -> shared "hidden" tile [pixel][channel];
+//   P0  wait for the patch's weight row (cp.async.bulk, own mbarrier: it was requested a whole patch ago);
+//   P1  re-stage W1/W3 -> UMMA operands B1/B2 with the BatchNorm scale folded in and the shift as an extra K column,
+//       W2 -> packed bf16x2 taps; only then wait for the x tile -- the (ph+2)x(pw+2) halo tile arrives through a 4-D
+//       tensor map (box starting 8 pixels left of the patch: TMA wants a 16-byte aligned innermost start; zero fill
+//       outside the image), so its flight time hides behind the weight re-stage -- patch the reflect halo of
+//       image-border patches in place and re-stage x -> operand A1 (K-major, lanes over pixels: conflict-free, with a
+//       constant-one channel that carries the BatchNorm shift);
+//   P2  GEMM1 on the tensor core: H[(ph+2)(pw+2) px x hid] = A1 . B1^T, M=128 tiles accumulated in TMEM, issued by an
+//       elected lane of warp 0 while an elected lane of warp 1 requests the next patch's weight row;
+//   P3  epilogue 1, tile by tile as the MMAs retire: TMEM -> registers -> ReLU6 -> bf16 -> shared "hidden" tile
+//       [pixel][channel];
 //   P4  depthwise 3x3 + BN2 + ReLU6 on CUDA cores in packed bf16x2 (lane = channel pair, warp = tile column,
 //       3x3 register window sliding down the column), written straight into GEMM2's A operand
 //       (128B-swizzled K-major);
