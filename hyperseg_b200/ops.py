@@ -63,8 +63,9 @@ def _require_inference(*tensors: torch.Tensor) -> None:
     if _needs_grad(*tensors):
         raise NotImplementedError(
             "this hyperseg_b200 operator is forward-only: gradients are implemented for the patch-wise convolutions "
-            "(MetaPatchConv2d / HyperPatchNoPadding / HyperPatchConv2d) and the weight heads, i.e. the hyperseg_v0_1 "
-            "training path; run the fused inverted-residual block under torch.no_grad() / model.eval()")
+            "(MetaPatchConv2d / HyperPatchNoPadding / HyperPatchConv2d) and the weight heads; the module "
+            "HyperPatchInvertedResidual differentiates through its stage-wise path, the fused kernel (ops.patch_ir) "
+            "itself must run under torch.no_grad() / on inputs that do not require grad")
 
 
 def _stream() -> int:

@@ -64,3 +64,43 @@ def test_gather_and_confusion_allreduce_gloo_world2(tmp_path, n_items):
     out = str(tmp_path / "r0.pt")
     mp.spawn(_worker, args=(2, _free_port(), n_items, out), nprocs=2, join=True)
     assert 0.0 <= torch.load(out)["miou"] <= 1.0
+
+
+def _train_worker(rank, world_size, port, tmp):
+    """Data-parallel training step (reference: DataParallel replicas, hyperseg/train.py; here one process per rank)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from hyperseg_b200.synthetic import build_model, synthetic_frames
+        from oracle.hyperseg_oracle import use_oracle_ops
+        torch.set_num_threads(4)
+        model = build_model("hyperseg-m", seed=0).train()
+        ddp = torch.nn.parallel.DistributedDataParallel(model)
+        frames = synthetic_frames(4, 64, 128, seed=3)
+        labels = torch.randint(0, 19, (4, 64, 128), generator=torch.Generator().manual_seed(1))
+        lo, hi = hdist.shard_bounds(4, rank, world_size)
+        torch.manual_seed(11 + rank)                       # drop-connect masks differ per rank, as per replica
+        with use_oracle_ops():
+            loss = torch.nn.functional.cross_entropy(ddp(frames[lo:hi]), labels[lo:hi])
+            loss.backward()
+        probe = ["decoder.level_4.0.signal2weights.weight", "decoder.level_0.0.0.signal2weights.weight",
+                 "weight_mapper.in_conv.0.weight", "backbone._conv_stem.weight"]
+        named = dict(model.named_parameters())
+        sums = torch.stack([named[n].grad.double().abs().sum() for n in probe])
+        assert all(p.grad is not None for p in model.parameters())
+        gathered = [torch.zeros_like(sums) for _ in range(world_size)]
+        dist.all_gather(gathered, sums)
+        assert all(torch.equal(g, gathered[0]) for g in gathered)      # gradients were all-reduced: identical replicas
+        assert torch.isfinite(sums).all() and (sums > 0).all()
+        if rank == 0:
+            torch.save({"loss": loss.item()}, tmp)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_training_step_gloo_world2(tmp_path):
+    out = str(tmp_path / "train.pt")
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert 0.0 < torch.load(out)["loss"] < 10.0

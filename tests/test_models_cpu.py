@@ -91,12 +91,34 @@ def test_forward_on_cpu_fails_loudly():
         model(synthetic_frames(1, 64, 128))
 
 
-def test_training_is_refused():
+def test_cpu_tensors_are_refused_under_autograd_too():
     from hyperseg_b200 import ops
     x = torch.zeros(1, 2, 2, 2, requires_grad=True)
     w = torch.zeros(1, 4, 1, 1)
     with pytest.raises((NotImplementedError, RuntimeError)):
         ops.patch_conv1x1(x, w, 2)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("config", ["hyperseg-m", "hyperseg-l-voc"])
+def test_engine_batchnorm_folding_preserves_logits(config, fused):
+    """What SegmentationEngine does to the static parts before it casts them: BatchNorm scale into the convolution,
+    shift into the bias or (fused epilogues) a FoldedBatchNorm -- same logits as the unfolded model."""
+    import copy
+    from hyperseg_b200.engine import fold_static_batchnorms
+    from hyperseg_b200.nn.efficientnet import FoldedBatchNorm
+    from oracle.hyperseg_oracle import use_oracle_ops
+    model = build_model(config).eval()
+    folded = copy.deepcopy(model)
+    n = fold_static_batchnorms(folded, fused_epilogues=fused)
+    assert n > 60
+    kept = [m for m in folded.backbone.modules() if isinstance(m, FoldedBatchNorm)]
+    assert (len(kept) > 60) == fused
+    assert not any(isinstance(m, torch.nn.BatchNorm2d) for m in folded.backbone.modules())
+    x = synthetic_frames(1, 128, 128)
+    with torch.no_grad(), use_oracle_ops():
+        ref, got = model(x), folded(x)
+    assert (got - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
 
 
 REFERENCE = "/root/reference"
