@@ -11,6 +11,8 @@ PyTorch calls channels_last -- ``(B, fh, fw, row)`` storage with ``row >= hp`` -
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _lib
@@ -197,23 +199,37 @@ def patch_ir(x, w, hidden, out_channels, bn1, bn2, bn3, residual=False):
     return y
 
 
-_PACKED_HEADS = {}      # (data_ptr, version, shape, groups) -> packed bf16 operand of a head's static weights
+# (data_ptr, version, shape, groups, dtype) -> (weak reference to the weight tensor that was packed, packed bf16 operand).
+# The weak reference ties an entry to one live tensor object: a different tensor that later lands on the same address
+# (same shape, version 0) must not be served the old operand.
+_PACKED_HEADS = {}
 
 
-def _packed_head(ws2d, sig_ch, groups):
+def _cache_lookup(cache, key, owner):
+    hit = cache.get(key)
+    if hit is not None and hit[0]() is owner:
+        return hit[1]
+    return None
+
+
+def _cache_store(cache, key, owner, value, limit=64):
+    if len(cache) > limit:
+        cache.clear()
+    cache[key] = (weakref.ref(owner), value)
+
+
+def _packed_head(ws2d, sig_ch, groups, owner):
     key = (ws2d.data_ptr(), ws2d._version, tuple(ws2d.shape), groups, ws2d.dtype)
-    hit = _PACKED_HEADS.get(key)
-    if hit is not None:
-        return hit
+    packed = _cache_lookup(_PACKED_HEADS, key, owner)
+    if packed is not None:
+        return packed
     n = _lib.load().hsb_head_packed_elems(sig_ch, ws2d.shape[0], groups)
     if n <= 0:
         raise ValueError("bad head dimensions")
     packed = torch.empty(n, dtype=torch.bfloat16, device=ws2d.device)
     _call("hsb_head_pack", ws2d.data_ptr(), packed.data_ptr(), None, sig_ch, ws2d.shape[0], groups,
           _DTYPES[ws2d.dtype], _stream())
-    if len(_PACKED_HEADS) > 64:
-        _PACKED_HEADS.clear()
-    _PACKED_HEADS[key] = packed
+    _cache_store(_PACKED_HEADS, key, owner, packed)
     return packed
 
 
@@ -232,6 +248,7 @@ def _signal2weights_fwd(s, ws, sig_index, sig_ch, hp, groups):
     dt = _compute_dtype(s)
     if s.dtype != dt:
         s = s.to(dt)
+    ws_owner = ws                                       # the caller's tensor object (normally the nn.Parameter)
     ws_src = ws.detach().reshape(ws.shape[0], -1)       # packed once per (tensor, version) on the tensor-core path
     ws = ws_src.to(dt).contiguous()
     B, C, fh, fw = s.shape
@@ -252,7 +269,7 @@ def _signal2weights_fwd(s, ws, sig_index, sig_ch, hp, groups):
     if dt == torch.bfloat16 and (fh * fw) % 8 == 0 and sp == 1 and st[0] % 8 == 0 and st[1] % 8 == 0 \
             and s.data_ptr() % 16 == 0 and (sig_ch // groups) <= 128 and not _NO_TC_HEADS:
         # tensor-core path: static weights packed once into the UMMA operand layout
-        packed = _packed_head(ws_src if (ws_src.dtype in _DTYPES and ws_src.is_contiguous()) else ws, sig_ch, groups)
+        packed = _packed_head(ws_src if (ws_src.dtype in _DTYPES and ws_src.is_contiguous()) else ws, sig_ch, groups, ws_owner)
         _call("hsb_signal2weights_packed_fwd", s.data_ptr(), packed.data_ptr(), buf.data_ptr(), B, sig_index, sig_ch,
               out_ch, hp, groups, fh, fw, st[0], st[1], row, _stream())
         return buf[..., :hp].permute(0, 3, 1, 2)

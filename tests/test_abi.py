@@ -87,3 +87,25 @@ def test_missing_library_raises(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libhsb200.so")
     with pytest.raises(_lib.HsbError, match="no CPU or PyTorch fallback"):
         _lib.load()
+
+
+def test_packed_head_cache_is_tied_to_the_live_tensor_object():
+    """The tensor-core head packs its static weights once per (tensor, version); an entry must not be served to
+    another tensor that later occupies the same address (key collision) nor survive its tensor."""
+    import gc
+    import torch
+    from hyperseg_b200 import ops
+    cache, key = {}, ("ptr", 0, (4, 2), 1, torch.float32)
+    a, b = torch.zeros(4, 2), torch.zeros(4, 2)
+    assert ops._cache_lookup(cache, key, a) is None
+    ops._cache_store(cache, key, a, "packed-a")
+    assert ops._cache_lookup(cache, key, a) == "packed-a"
+    assert ops._cache_lookup(cache, key, b) is None            # same key, other tensor object: miss
+    ops._cache_store(cache, key, b, "packed-b")
+    assert ops._cache_lookup(cache, key, b) == "packed-b" and ops._cache_lookup(cache, key, a) is None
+    del b
+    gc.collect()
+    assert cache[key][0]() is None                               # dead owner: the entry can never hit again
+    for i in range(70):                                          # bounded
+        ops._cache_store(cache, ("k", i), a, i)
+    assert len(cache) <= 66
