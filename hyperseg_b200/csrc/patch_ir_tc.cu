@@ -564,13 +564,55 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                     for (int kx = 0; kx < 3; ++kx) { a0r[kx] = a1r[kx]; a1r[kx] = a2r[kx]; b0r[kx] = b1r[kx]; b1r[kx] = b2r[kx]; }
                 }
             };
+#ifdef HSB_IR_DW2
+            // experiment: two ADJACENT tile columns per thread -- the 3x3 windows overlap, so a
+            // row step costs 4 shared loads instead of 6 -- and one FMA chain per output (bias as the initial value)
+            auto column_adjacent = [&](int cp, int v, unsigned char* dsta, unsigned char* dstb, int dst_step) {
+                __nv_bfloat162 wt[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) wt[k] = *reinterpret_cast<const __nv_bfloat162*>(&w2p[k * C::HPW + cp]);
+                const __nv_bfloat162 bias = *reinterpret_cast<const __nv_bfloat162*>(&w2p[9 * C::HPW + cp]);
+                const uint32_t* col = hid + v * C::HPW + cp;               // hidden pixel (r, v + j) at (r*TW + v + j)*HPW
+                __nv_bfloat162 r0[4], r1[4], r2[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t t0 = col[(0 * C::TW + j) * C::HPW], t1 = col[(1 * C::TW + j) * C::HPW];
+                    r0[j] = *reinterpret_cast<__nv_bfloat162*>(&t0); r1[j] = *reinterpret_cast<__nv_bfloat162*>(&t1);
+                }
+#pragma unroll
+                for (int u = 0; u < C::PH; ++u) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t t2 = col[((u + 2) * C::TW + j) * C::HPW];
+                        r2[j] = *reinterpret_cast<__nv_bfloat162*>(&t2);
+                    }
+                    __nv_bfloat162 pa = bias, pb = bias;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        pa = __hfma2(wt[kx], r0[kx], pa);         pb = __hfma2(wt[kx], r0[kx + 1], pb);
+                        pa = __hfma2(wt[3 + kx], r1[kx], pa);     pb = __hfma2(wt[3 + kx], r1[kx + 1], pb);
+                        pa = __hfma2(wt[6 + kx], r2[kx], pa);     pb = __hfma2(wt[6 + kx], r2[kx + 1], pb);
+                    }
+                    pa = __hmin2(__hmax2(pa, zero), six);
+                    pb = __hmin2(__hmax2(pb, zero), six);
+                    *reinterpret_cast<uint32_t*>(dsta + u * dst_step) = *reinterpret_cast<uint32_t*>(&pa);
+                    *reinterpret_cast<uint32_t*>(dstb + u * dst_step) = *reinterpret_cast<uint32_t*>(&pb);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
+                }
+            };
+#endif
             if (warp < C::DWW) {
                 if (lane < C::MAINP) {
                     const int cp = lane;
                     // pixel m = u*PW + v: 128-byte swizzled row m, 16-byte chunk (cp/4) ^ (m%8); m%8 == v%8 for all u
                     auto a2_dst = [&](int v) { return sm + C::OFF_A2 + v * 128 + ((((cp >> 2) ^ (v & 7)) << 4) | ((cp & 3) << 2)); };
                     if (C::PW == 2 * C::DWW) {
+#ifdef HSB_IR_DW2
+                        column_adjacent(cp, 2 * warp, a2_dst(2 * warp), a2_dst(2 * warp + 1), C::PW * 128);
+#else
                         column_pair(cp, warp, warp + C::DWW, a2_dst(warp), a2_dst(warp + C::DWW), C::PW * 128);
+#endif
                     } else {
 #pragma unroll 1
                         for (int v = warp; v < C::PW; v += C::DWW) column(cp, v, a2_dst(v), C::PW * 128);
