@@ -742,7 +742,13 @@ static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
     // 5-D view (innermost first): 8 pixels | channel | 8-pixel chunk of the row | row | image
     CUtensorMap map, hmap;
     const cuuint64_t dims[5] = {8, (cuuint64_t)C::CIN, (cuuint64_t)p.W / 8, (cuuint64_t)p.H, (cuuint64_t)p.B};
-    const cuuint64_t strides[4] = {(cuuint64_t)p.W * p.H * 2, 16, (cuuint64_t)p.W * 2, (cuuint64_t)p.W * p.H * C::CIN * 2};
+    // HSB_IR_XBLOCKED=1: x is stored (B, H, W/8, C, 8) -- the layout a fused level-input kernel would write -- so that a
+    // (row, chunk) of the box is ONE contiguous run of C*16 bytes instead of C separate 16-byte rows
+    static const bool blocked = [] { const char* v = getenv("HSB_IR_XBLOCKED"); return v && v[0] == '1'; }();
+    const cuuint64_t s_nchw[4] = {(cuuint64_t)p.W * p.H * 2, 16, (cuuint64_t)p.W * 2, (cuuint64_t)p.W * p.H * C::CIN * 2};
+    const cuuint64_t s_blk[4] = {16, (cuuint64_t)C::CIN * 16, (cuuint64_t)(p.W / 8) * C::CIN * 16,
+                                 (cuuint64_t)p.H * (p.W / 8) * C::CIN * 16};
+    const cuuint64_t* strides = blocked ? s_blk : s_nchw;
     const cuuint32_t box[5] = {8, (cuuint32_t)C::K1, (cuuint32_t)C::XCH, (cuuint32_t)C::TH, 1};
     const cuuint32_t hbox[5] = {8, (cuuint32_t)C::K1, 1, (cuuint32_t)C::TH, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};

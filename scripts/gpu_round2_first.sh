@@ -16,3 +16,6 @@ for v in x5d dw2; do
     HSB_LIBRARY=$L/libhsb200_$v.so timeout 300 python scripts/time_kernel.py ir ir3 2>&1 | tail -1
   fi
 done
+if [ -f $L/libhsb200_x5d.so ]; then
+  HSB_LIBRARY=$L/libhsb200_x5d.so HSB_IR_XBLOCKED=1 timeout 300 python scripts/x5d_blocked_check.py 2>&1 | tail -4
+fi
