@@ -19,3 +19,7 @@ done
 if [ -f $L/libhsb200_x5d.so ]; then
   HSB_LIBRARY=$L/libhsb200_x5d.so HSB_IR_XBLOCKED=1 timeout 300 python scripts/x5d_blocked_check.py 2>&1 | tail -4
 fi
+# (3) experimental fused depthwise conv of the encoder (engine flag), parity then A/B of the whole step
+HSB_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_ops_gpu.py -m gpu -q -k "depthwise" 2>&1 | tail -4
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-160
+HSB_FUSED_DW=1 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-160
