@@ -25,6 +25,7 @@ _F = c_void_p  # float* passed as raw device address (None -> NULL)
 SIGNATURES = {
     "hsb_version": [],
     "hsb_last_error": [],
+    "hsb_last_kernel": [],
     "hsb_device_info": [POINTER(c_int), POINTER(c_int)],
     "hsb_patch_conv1x1_fwd": [c_void_p, c_void_p, c_void_p, _F, _F, c_int,
                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -32,6 +33,12 @@ SIGNATURES = {
     "hsb_patch_ir_fwd": [c_void_p, c_void_p, c_void_p, _F, _F, _F, _F, _F, _F,
                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                          c_int, c_int, c_int, c_int64, c_void_p],
+    "hsb_ir_arranged_row_elems": [c_int, c_int, c_int],
+    "hsb_patch_ir_arranged_supported": [c_int, c_int, c_int, c_int],
+    "hsb_ir_arrange_weights": [c_void_p, c_void_p, _F, _F, _F, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_int64, c_void_p],
+    "hsb_patch_ir_arranged_fwd": [c_void_p, c_void_p, c_void_p, _F, _F, _F,
+                                  c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_void_p],
     "hsb_signal2weights_fwd": [c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_int64, c_int64, c_int64, c_int, c_int, c_int64, c_void_p],
@@ -66,6 +73,8 @@ SIGNATURES = {
     "hsb_dwconv_bias_act_nhwc_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 13 + [c_void_p],
 }
 
+_INT64_RESULTS = ("hsb_head_packed_elems", "hsb_ir_arranged_row_elems")
+
 _lib = None
 
 
@@ -86,7 +95,8 @@ def load() -> ctypes.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.argtypes = argtypes
-        fn.restype = c_char_p if name == "hsb_last_error" else (c_int64 if name == "hsb_head_packed_elems" else c_int)
+        fn.restype = c_char_p if name in ("hsb_last_error", "hsb_last_kernel") else (
+            c_int64 if name in _INT64_RESULTS else c_int)
     _lib = lib
     return lib
 
@@ -95,6 +105,12 @@ def check(status: int, what: str) -> None:
     if status != 0:
         msg = load().hsb_last_error()
         raise HsbError(f"{what} failed with status {status}: {msg.decode() if msg else '?'}")
+
+
+def last_kernel() -> str:
+    """Name of the kernel the last entry point called from this thread launched (hsb_last_kernel)."""
+    name = load().hsb_last_kernel()
+    return name.decode() if name else ""
 
 
 def version() -> int:

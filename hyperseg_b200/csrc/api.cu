@@ -7,6 +7,9 @@
 namespace hsb {
 
 static thread_local std::string g_last_error;
+static thread_local const char* g_last_kernel = "";
+
+void note_kernel(const char* name) { g_last_kernel = name; }
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -45,6 +48,8 @@ extern "C" {
 int hsb_version(void) { return HSB200_VERSION; }
 
 const char* hsb_last_error(void) { return hsb::g_last_error.c_str(); }
+
+const char* hsb_last_kernel(void) { return hsb::g_last_kernel; }
 
 int hsb_device_info(int* sm_count, int* compute_capability) {
     int n = 0;

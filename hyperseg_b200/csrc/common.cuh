@@ -14,6 +14,7 @@ void set_error(const std::string& msg);           // stores into the thread-loca
 int fail(int code, const std::string& msg);       // set_error + return code
 int check_launch(const char* what);               // cudaGetLastError -> status
 int device_sm_count();                            // cached per device
+void note_kernel(const char* name);               // records which kernel an entry point chose (hsb_last_kernel)
 
 #define HSB_REQUIRE(cond, code, msg)                         \
     do {                                                     \

@@ -199,6 +199,61 @@ def patch_ir(x, w, hidden, out_channels, bn1, bn2, bn3, residual=False):
     return y
 
 
+def ir_arranged_supported(cin, hidden, out_channels, patch_size) -> bool:
+    """True when the restage-free tensor-core MetaBlock kernel has an instantiation for this shape."""
+    return bool(_lib.load().hsb_patch_ir_arranged_supported(int(cin), int(hidden), int(out_channels), int(patch_size)))
+
+
+def ir_arranged_row(cin, hidden, out_channels) -> int:
+    """bf16 elements of one arranged weight row (csrc/ir_arranged.cuh)."""
+    return int(_lib.load().hsb_ir_arranged_row_elems(int(cin), int(hidden), int(out_channels)))
+
+
+def ir_arrange_weights(w, cin, hidden, out_channels, s1, s2, s3):
+    """Reference-order per-patch weights (B, hp, fh, fw) -> arranged rows (B, fh, fw, row) bf16 with the three
+    BatchNorm scales folded in: the operand order of :func:`patch_ir_arranged`."""
+    _require_cuda(w)
+    if w.dtype not in _DTYPES:
+        w = w.float()
+    w, layout, row = weight_layout(w)
+    B, hp, fh, fw = w.shape
+    if hp != cin * hidden + 9 * hidden + hidden * out_channels:
+        raise ValueError(f"expected {cin * hidden + 9 * hidden + hidden * out_channels} weights per patch, got {hp}")
+    s1, _ = _affine(s1, s1, hidden, w.device)
+    s2, _ = _affine(s2, s2, hidden, w.device)
+    s3, _ = _affine(s3, s3, out_channels, w.device)
+    out = torch.empty((B, fh, fw, ir_arranged_row(cin, hidden, out_channels)), dtype=torch.bfloat16, device=w.device)
+    _call("hsb_ir_arrange_weights", w.data_ptr(), out.data_ptr(), s1.data_ptr(), s2.data_ptr(), s3.data_ptr(),
+          B, cin, hidden, out_channels, fh, fw, _DTYPES[w.dtype], layout, row, _stream())
+    return out
+
+
+def patch_ir_arranged(x, w_arranged, hidden, out_channels, b1, b2, b3):
+    """Fused MetaBlock on arranged weight rows (B, fh, fw, row): bf16, tcgen05 path only -- raises for shapes without an
+    instantiation instead of switching kernels.  b1/b2/b3 are the BatchNorm shifts (the scales live in the rows)."""
+    _require_cuda(x, w_arranged)
+    _require_inference(x, w_arranged)
+    if x.dtype != torch.bfloat16 or w_arranged.dtype != torch.bfloat16:
+        raise TypeError("patch_ir_arranged is a bf16 kernel")
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    if w_arranged.dim() != 4 or w_arranged.shape[0] != B or w_arranged.stride(3) != 1:
+        raise ValueError("arranged weights must be (B, fh, fw, row) with contiguous rows")
+    fh, fw, row = w_arranged.shape[1:]
+    rs = w_arranged.stride(2) if fw > 1 else (w_arranged.stride(1) if fh > 1 else w_arranged.stride(0))
+    if (fw > 1 and fh > 1 and w_arranged.stride(1) != fw * rs) or (B > 1 and w_arranged.stride(0) != fh * fw * rs):
+        raise ValueError("arranged weight rows must be uniformly strided")
+    if row < ir_arranged_row(Cin, hidden, out_channels):
+        raise ValueError("arranged rows are too short for this block")
+    _, b1 = _affine(b1, b1, hidden, x.device)
+    _, b2 = _affine(b2, b2, hidden, x.device)
+    _, b3 = _affine(b3, b3, out_channels, x.device)
+    y = torch.empty((B, out_channels, H, W), dtype=torch.bfloat16, device=x.device)
+    _call("hsb_patch_ir_arranged_fwd", x.data_ptr(), w_arranged.data_ptr(), y.data_ptr(), b1.data_ptr(), b2.data_ptr(),
+          b3.data_ptr(), B, Cin, hidden, out_channels, H, W, fh, fw, rs, _stream())
+    return y
+
+
 # (data_ptr, version, shape, groups, dtype) -> (weak reference to the weight tensor that was packed, packed bf16 operand).
 # The weak reference ties an entry to one live tensor object: a different tensor that later lands on the same address
 # (same shape, version 0) must not be served the old operand.

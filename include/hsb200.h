@@ -56,6 +56,10 @@ typedef enum hsb_padmode { HSB_PAD_ZEROS = 0, HSB_PAD_REFLECT = 1, HSB_PAD_REPLI
 /* Library / build introspection. */
 int hsb_version(void);
 const char* hsb_last_error(void);
+/* Name of the CUDA kernel the last successful entry point of the calling thread launched ("" before the first call).
+ * Entry points that choose between kernels (tensor-core vs CUDA-core paths) record their choice here, so a caller --
+ * and the parity tests -- can assert which one ran. */
+const char* hsb_last_kernel(void);
 /* Writes the number of SMs and the compute capability (major*10+minor) of the current
  * device; HSB_ERR_NO_DEVICE when there is none. */
 int hsb_device_info(int* sm_count, int* compute_capability);
@@ -91,6 +95,32 @@ int hsb_patch_ir_fwd(const void* x, const void* w, void* y,
                      const float* bn3_scale, const float* bn3_shift,
                      int B, int Cin, int hid, int Cout, int H, int W, int fh, int fw,
                      int residual, int dtype, int w_layout, int64_t w_row_stride, void* stream);
+
+/*
+ * Restage-free tensor-core form of the same MetaBlock (bf16; tcgen05 / TMEM / TMA; csrc/patch_ir2.cu).  The per-patch
+ * weights come as "arranged" rows: the numbers of [W1 | W2 | W3] with the three BatchNorm scales folded in, ordered as
+ * the kernel's UMMA operands (csrc/ir_arranged.cuh):
+ *   B1 [ceil(Cin/8)][hid][8] = bn1_scale[n]*W1[n][k] | W2T [9][hid] = bn2_scale[c]*W2[c][tap] (padded to 16 B) |
+ *   B2 [ceil(hid/8)][Cout][8] = bn3_scale[n]*W3[n][k],   zero where k runs past Cin / hid.
+ *   hsb_ir_arranged_row_elems      bf16 elements of one arranged row (-1 on bad dimensions)
+ *   hsb_patch_ir_arranged_supported  1 when (Cin, hid, Cout, patch size) has an instantiation
+ *   hsb_ir_arrange_weights         reference-order weights (fp32 / bf16, either layout) -> arranged rows, row stride
+ *                                  hsb_ir_arranged_row_elems; the weight head can also emit arranged rows directly
+ *                                  (hsb_head_pack_arranged / hsb_signal2weights_packed_fwd)
+ *   hsb_patch_ir_arranged_fwd      y = bn3(W3 . relu6(bn2(dw3x3(relu6(bn1(W1 . tile))))));  x, y bf16 NCHW, 16-byte
+ *                                  aligned, W % 8 == 0; square 16x16 or 8x8 patches; no residual.
+ * Replaces HyperPatchInvertedResidual.conv (hyperseg/models/hyperseg_v1_0.py:328-370, hyperseg_v1_0_unify.py:342-389).
+ */
+int64_t hsb_ir_arranged_row_elems(int Cin, int hid, int Cout);
+int hsb_patch_ir_arranged_supported(int Cin, int hid, int Cout, int patch_size);
+int hsb_ir_arrange_weights(const void* w, void* w_arranged,
+                           const float* bn1_scale, const float* bn2_scale, const float* bn3_scale,
+                           int B, int Cin, int hid, int Cout, int fh, int fw,
+                           int dtype, int w_layout, int64_t w_row_stride, void* stream);
+int hsb_patch_ir_arranged_fwd(const void* x, const void* w_arranged, void* y,
+                              const float* bn1_shift, const float* bn2_shift, const float* bn3_shift,
+                              int B, int Cin, int hid, int Cout, int H, int W, int fh, int fw,
+                              int64_t w_row_stride, void* stream);
 
 /*
  * Weight head: grouped 1x1 convolution from the signal map to per-patch weights.

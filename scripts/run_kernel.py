@@ -20,6 +20,12 @@ elif which == "ir3":
     x = rnd(B, cin, h, w); wt = ops.weights_to_patch_major(rnd(B, cin * hid + 9 * hid + hid * cout, 16, 32, scale=0.3))
     b1, b2, b3 = bn(hid), bn(hid), bn(cout)
     fn = lambda: ops.patch_ir(x, wt, hid, cout, b1, b2, b3)
+elif which in ("ir2", "ir2_3"):
+    cin, hid, cout, h, w = (34, 68, 19, 256, 512) if which == "ir2" else (24, 48, 16, 128, 256)
+    x = rnd(B, cin, h, w); wt = ops.weights_to_patch_major(rnd(B, cin * hid + 9 * hid + hid * cout, 16, 32, scale=0.3))
+    b1, b2, b3 = bn(hid), bn(hid), bn(cout)
+    wa = ops.ir_arrange_weights(wt, cin, hid, cout, b1[0], b2[0], b3[0])
+    fn = lambda: ops.patch_ir_arranged(x, wa, hid, cout, b1[1], b2[1], b3[1])
 elif which == "conv0":
     x = rnd(B, 82, 16, 32); wt = ops.weights_to_patch_major(rnd(B, 82 * 64, 16, 32, scale=0.3)); sc, sh = bn(64)
     fn = lambda: ops.patch_conv1x1(x, wt, 64, 1, sc, sh, "relu")
