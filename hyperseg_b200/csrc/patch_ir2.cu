@@ -1,29 +1,37 @@
-// Fused patch-wise inverted-residual MetaBlock, restage-free tensor-core kernel (tcgen05 / TMEM / TMA), bf16.
+// Fused patch-wise inverted-residual MetaBlock, restage-free warp-specialised tensor-core kernel
+// (tcgen05 / TMEM / TMA / mbarrier pipelines), bf16.
 //
 // Same arithmetic as the reference's HyperPatchInvertedResidual.conv (hyperseg/models/hyperseg_v1_0.py:328-370,
 // hyperseg_v1_0_unify.py:342-389): reflect pad 1 -> (ph+2)x(pw+2) halo tile -> W1.tile, BN1, ReLU6 -> depthwise 3x3
-// (valid), BN2, ReLU6 -> W3., BN3.  What is different from patch_ir_tc.cu (round 1): no thread ever re-stages an
-// operand.
+// (valid), BN2, ReLU6 -> W3., BN3.  No thread ever re-stages an operand:
 //
 //   x tile    The body of the halo tile ((ps+2) rows x ps pixels) is loaded by TMA through a 5-D view of NCHW x,
 //             dims {W, c%8, H, c/8, B}, box {ps, 8, ps+2, 1, 1}, SWIZZLE_32B (ps = 16) / no swizzle (ps = 8).  It lands
 //             as [c/8][row][c%8][ps px], which IS the canonical MN-major UMMA A operand: M-group = one tile row,
 //             K rows 32 (16) bytes apart.  Rows outside the image are TMA zero fill and replaced by their mirror row
-//             for border patches.  The 2(ps+2) halo-column pixels are read from global memory one patch ahead
-//             (2-byte loads, reflection in the index) and stored into three extra M-groups.
+//             for border patches.  The 2(ps+2) halo-column pixels are read from global memory (2-byte loads,
+//             reflection in the index) and stored into extra M-groups.
 //   weights   The row of a patch arrives in "arranged" order (ir_arranged.cuh): B1 and B2 are K-major UMMA B
 //             operands as they lie, W2T is [tap][channel]; BatchNorm scales are already folded in (by the weight
 //             head that produced the row or by hsb_ir_arrange_weights).  Two bulk copies per patch.
 //   shifts    BN1 / BN3 shifts: one constant "init" MMA per accumulator tile, D = Ones(128x16) . ShiftB, before the
 //             data MMAs accumulate on top.  BN2 shift: initial value of the depthwise accumulation.
-//   GEMM1     H[(ps+2)^2 px x hid] in TMEM, M = 128 tiles; epilogue 1 = ReLU6 + bf16 -> shared hidden tile.
-//   depthwise packed bf16x2 on CUDA cores, thread = 4 channels x 2 adjacent columns x 4 rows, 8-byte shared loads /
-//             stores, written straight into GEMM2's 128B-swizzled A operand, half a patch (one M tile) at a time so
-//             that GEMM2 of the first half runs under the depthwise of the second.
-//   GEMM2     O[ps*ps px x Cout]; epilogue 2 = bf16 -> shared [c][u][v] tile -> ONE TMA store per patch (NCHW).
 //
-// Persistent CTAs, two (ps = 16) or up to six (ps = 8) per SM; four CTA-wide barriers per patch; x / weight loads
-// for patch i+1 are issued as soon as GEMM1 of patch i has retired, so they fly under everything else.
+// One persistent CTA per SM; its warps are specialised and hand patches to each other through mbarriers, every
+// buffer between two roles exists twice, so all roles work on different patches at the same time:
+//
+//   producers (3 warps)   lane 0 of the first: TMA x tile + bulk weight rows into stage s;  all 96 lanes: halo-column
+//                         pixels (+ mirror rows of border patches) -> A1[s]
+//   MMA1 (1 thread)       GEMM1: H[(ps+2)^2 px x hid] = A1[s] . B1[s]^T (+ shift) -> TMEM ACC1[s], one commit per M tile
+//   epilogue 1 (4 warps)  ACC1[s] -> ReLU6 -> bf16 -> hidden tile HID[s] ([pixel][channel])
+//   depthwise (8-9 warps) HID[s] -> 3x3 + BN2 + ReLU6 in packed bf16x2 (thread = 4 channels x 2 adjacent columns x 4
+//                         rows, 8-byte shared loads / stores) -> GEMM2's 128B-swizzled A operand A2[h], one M tile
+//                         (half a 16x16 patch) at a time
+//   MMA2 (1 thread)       GEMM2: O[128 px x Cout] = A2[h] . B2[s]^T (+ shift) -> TMEM ACC2
+//   epilogue 2 (4 warps)  ACC2 -> bf16 -> output staging tile [c][u][v] (inside the consumed A2[h]) -> one TMA store
+//
+// The depthwise warps carry ~60 % of the CUDA-core instructions of a patch, so they set the pace; everything else runs
+// ahead of / behind them on other patches.
 #include <cuda.h>
 
 #include <cstdio>
@@ -45,46 +53,71 @@ struct IR2 {
     static constexpr int B1_LBO = HID * 16, B2_LBO = COUT * 16;
     static constexpr int SZ_B1 = KC1 * B1_LBO, SZ_W2T = ir_r16(18 * HID), SZ_B2 = KC2 * B2_LBO;
     static constexpr int ROW_BYTES = SZ_B1 + SZ_W2T + SZ_B2;
-    // GEMM shapes
-    static constexpr int K1 = ir_r16(CIN), N1 = ir_r16(HID), K2 = ir_r16(HID), N2 = ir_r16(COUT);
-    // A1 (MN-major): M-group = PS pixels of one channel row group; k-group = 8 channels
+    // GEMM shapes.  K holds one channel more than the data: a constant-one channel in the first 8-channel group past
+    // the data (k-group KC1 of A1, channel 8 KC2 of A2) meets the BatchNorm shift in the matching row of B1 / B2.  Both
+    // live in bytes that no copy ever overwrites, so they are written once per kernel.
+    static constexpr int K1 = ir_r16(8 * KC1 + 1), N1 = ir_r16(HID), K2 = ir_r16(8 * KC2 + 1), N2 = ir_r16(COUT);
+    static constexpr int ONE2 = 8 * KC2;                       // the constant-one channel of A2
+    // A1 (MN-major): M-group = PS pixels of one tile row (or PS halo pixels); k-group = 8 channels
     static constexpr int ROWB = PS * 2, GRP = 8 * ROWB;
     static constexpr int HALO = 2 * TH, HALO_G = (HALO + PS - 1) / PS, MG = TH + HALO_G;
     static constexpr int A1_MGS = GRP, A1_KGS = MG * GRP;
     static constexpr int GPT = 128 / PS;                       // M-groups per 128-row tile
-    static constexpr int BODY = TH * PS, T = BODY + HALO, M1T = (T + 127) / 128;
-    static constexpr int SZ_A1 = ir_r1024(KC1 * A1_KGS);       // the bytes that follow (A2) only ever hold finite bf16
+    // M tiles of GEMM1: NBT tiles of body rows [0, LO_ROWS), then one tile that starts at group LO_ROWS and holds the
+    // remaining HI_ROWS body rows and the halo groups.  The body tiles do not depend on the neighbours' tiles.
+    static constexpr int LO_ROWS = PS == 16 ? 16 : TH, HI_ROWS = TH - LO_ROWS;
+    static constexpr int NBT = (LO_ROWS * PS + 127) / 128, M1T = NBT + 1;
+    static constexpr int T = TH * TH;                          // pixels of the halo tile
+    static constexpr int SZ_A1 = ir_r1024((K1 / 8 - 1) * A1_KGS + (LO_ROWS + GPT) * GRP);     // incl. what the last tile over-reads
     // A2: one 128-row tile = RPH output rows
     static constexpr int OUT_PX = PS * PS, M2T = (OUT_PX + 127) / 128;
     static constexpr int RPH = PS / M2T;                        // output rows per half
-    static constexpr int RQ = RPH / 2;                          // output rows per depthwise thread
+    static constexpr int HALF_PX = RPH * PS;                    // output pixels per half (128 or 64)
     static constexpr int SZ_A2S = 128 * 128, KT2 = K2 > 64 ? K2 - 64 : 0;
     static constexpr int A2T_LBO = 128 * 16, SZ_A2T = (KT2 / 8) * A2T_LBO;
-    static constexpr int SZ_A2 = SZ_A2S + SZ_A2T;
-    static constexpr int SZ_YST = COUT * OUT_PX * 2;            // output staging tile [c][u][v], inside A2
+    static constexpr int SZ_A2 = ir_r1024(SZ_A2S + SZ_A2T);
+    static constexpr int SZ_YST = COUT * HALF_PX * 2;           // output staging tile [c][u][v] of one half, inside A2
     // hidden tile [pixel][channel]
     static constexpr int HPITCH = ir_r8(HID) * 2, SZ_HID = ir_r128(T * HPITCH);
-    // weight buffers: what the descriptors read past the data must be zero
+    // weight buffers: what the descriptors read past the data is zero, except the shift row
     static constexpr int SZ_W1 = ir_r128(ir_max(SZ_B1, (K1 / 8 - 1) * B1_LBO + N1 * 16));
     static constexpr int SZ_W23 = ir_r128(SZ_W2T + ir_max(SZ_B2, (K2 / 8 - 1) * B2_LBO + N2 * 16));
-    static constexpr int SZ_SHB1 = 2 * N1 * 16, SZ_SHB2 = 2 * N2 * 16;
+    static constexpr int SZ_SAVE = ir_r128(CIN * TH * 2);       // body column PS-1 of a tile: the left halo column of the next patch
     static constexpr int MAINQ = ir_min(16, HID / 4), TAILQ = HID / 4 - MAINQ;
-    static constexpr int DWW = PS / 2;                          // main depthwise warps: one per column pair
-    static constexpr int WARPS = DWW + (TAILQ > 0 ? 1 : 0), THREADS = 32 * WARPS;
-    static constexpr int NH = (HALO * CIN + THREADS - 1) / THREADS;   // halo pixels per thread
-    static constexpr int TMEM_COLS = ir_pow2_cols(ir_max(M1T * N1, M2T * N2));
-    // shared memory map (bytes from a 1024-aligned base)
-    static constexpr int OFF_A1 = 0, OFF_A2 = OFF_A1 + SZ_A1, OFF_HID = OFF_A2 + ir_r1024(SZ_A2);
-    static constexpr int OFF_W1 = OFF_HID + SZ_HID, OFF_W23 = OFF_W1 + SZ_W1;
-    static constexpr int OFF_SHB1 = OFF_W23 + SZ_W23, OFF_SHB2 = OFF_SHB1 + SZ_SHB1, OFF_ONES = OFF_SHB2 + SZ_SHB2;
-    static constexpr int OFF_B2B = OFF_ONES + 128, OFF_BAR = OFF_B2B + ir_r16(HID * 2);
-    static constexpr int USED_BYTES = OFF_BAR + 128, SMEM_BYTES = USED_BYTES + 1024;
-    static constexpr int CTAS = ir_max(1, ir_min(ir_min((228 * 1024 - 1024) / (SMEM_BYTES + 1024), 512 / TMEM_COLS), PS == 16 ? 2 : 6));
+    // warp roles
+    static constexpr int W_EPI1 = 0, W_EPI2 = 4, W_DW = 8;
+    // depthwise threads: 4 channels x a strip of WT columns x RPT rows; a warp = 16 channel quads x 2 strips, a half
+    // takes WPH warps and both halves of a 16x16 patch run side by side.  The 17th channel quad of a 68-wide hidden
+    // layer (TAILQ) is spread over the even lanes, one pixel each.
+#ifndef HSB_IR_WT
+#define HSB_IR_WT 4
+#endif
+#ifndef HSB_IR_RPT
+#define HSB_IR_RPT 8
+#endif
+    static constexpr int WT = PS == 16 ? HSB_IR_WT : 2, STRIPS = PS / WT, RPT = PS == 16 ? HSB_IR_RPT : 4, RG = RPH / RPT, WPH = STRIPS / 2 * RG;
+    static constexpr int DWMAIN = WPH * M2T, DWN = DWMAIN;
+    static constexpr int W_PROD = W_DW + DWN, PRODN = 4;                         // halo / mirror-row warps
+    static constexpr int W_MMA1 = W_PROD + PRODN, W_MMA2 = W_MMA1 + 1, W_LOAD = W_MMA2 + 1;
+    static constexpr int WARPS = W_LOAD + 1, THREADS = 32 * WARPS;
+    static constexpr int ACC1_COLS = M1T * N1, ACC2_COL = 2 * ACC1_COLS;
+    static constexpr int TMEM_COLS = ir_pow2_cols(ACC2_COL + N2);
+    // shared memory map (bytes from a 1024-aligned base); [2] = two stages
+    static constexpr int OFF_A1 = 0, OFF_A2 = OFF_A1 + 2 * SZ_A1, OFF_HID = OFF_A2 + 2 * SZ_A2;
+    static constexpr int OFF_W1 = OFF_HID + 2 * SZ_HID, OFF_W23 = OFF_W1 + 2 * SZ_W1;
+    static constexpr int OFF_SAVE = OFF_W23 + 2 * SZ_W23;
+    static constexpr int OFF_B2B = OFF_SAVE + 2 * SZ_SAVE, OFF_BAR = OFF_B2B + ir_r16(HID * 2);
+    static constexpr int NBAR = 40;
+    static constexpr int USED_BYTES = OFF_BAR + NBAR * 8 + 16, SMEM_BYTES = USED_BYTES + 1024;
+    static constexpr int CTAS = 1;
     static_assert(PS == 16 || PS == 8, "patch size");
     static_assert(HID % 4 == 0 && TAILQ <= 1, "hidden width: multiple of 4, at most 68");
     static_assert(SZ_YST <= SZ_A2S, "output staging tile must fit the swizzled part of A2");
-    static_assert((K1 / 8 - KC1) * A1_KGS + GPT * GRP <= SZ_A2, "GEMM1 over-read must stay inside A2");
-    static_assert(3 + M1T + M2T <= 12, "barrier slots");
+    static_assert(HI_ROWS * PS + HALO <= 128, "the rest of the body and the halo pixels must fit one M tile");
+    static_assert(M1T <= 3 && M2T <= 2, "barrier slots");
+    static_assert(ONE2 < 64 ? ONE2 / 4 < 16 && ONE2 >= HID : true, "constant-one channel of A2");
+    static_assert(TMEM_COLS <= 512, "TMEM budget");
+    static_assert(SZ_A1 <= 65536, "A1 offsets are packed in 16 bits");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -95,14 +128,21 @@ struct IR2Params {
     int B, H, W, fh, fw, total;
     int64_t w_row_stride;        // elements between rows
 #ifdef HSB_IR_PROF
-    long long* prof;             // [grid][16] per-phase cycle sums of thread 0 (profiling build only)
+    long long* prof;             // [grid][8 roles][8] wait-cycle sums of one lane per role (profiling build only)
 #endif
 };
 
+struct IR2Maps { CUtensorMap lo, lo_tail, hi, hi_tail, y; };   // x boxes of LO_ROWS / HI_ROWS rows (8-channel groups / last partial group), y box
+
+// profiling build: cycles a role's lane spends in each of its waits, and in its whole loop
 #ifdef HSB_IR_PROF
-#define HSB_STAMP(k) do { if (tid == 0) { long long now_ = clock64(); prof_acc[k] += now_ - prof_t; prof_t = now_; } } while (0)
+#define PWAIT(slot, bar, par) do { long long t0_ = clock64(); mbar_wait_suspend(bar, par); prof_acc[slot] += clock64() - t0_; } while (0)
+#define PROF_BEGIN() long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64()
+#define PROF_END(role, cond) do { if (cond) { prof_acc[7] = clock64() - prof_t0; for (int k_ = 0; k_ < 8; ++k_) p.prof[((size_t)blockIdx.x * 8 + role) * 8 + k_] = prof_acc[k_]; } } while (0)
 #else
-#define HSB_STAMP(k) do { } while (0)
+#define PWAIT(slot, bar, par) mbar_wait_suspend(bar, par)
+#define PROF_BEGIN() do { } while (0)
+#define PROF_END(role, cond) do { } while (0)
 #endif
 
 __device__ __forceinline__ uint32_t relu6_pack(float lo, float hi) {
@@ -120,414 +160,600 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-    return v;
-}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 constexpr uint32_t SWZ_32B_MODE = 6;
 
+// Each CTA owns a contiguous run of patches in row-major (image, patch row, patch column) order, so that consecutive
+// patches are horizontal neighbours: the halo columns of a patch are then columns of its neighbours' tiles, which are (or
+// are about to be) in shared memory.  patch index -> (image, patch row, patch column) without a division per patch.
+struct PatchWalk {
+    int patch, b, pi, pj;
+    __device__ __forceinline__ void init(int first, int fh, int fw) {
+        const int P = fh * fw;
+        patch = first; b = first / P; pi = (first % P) / fw; pj = first % fw;
+    }
+    __device__ __forceinline__ void next(int fh, int fw) {
+        ++patch;
+        if (++pj == fw) { pj = 0; if (++pi == fh) { pi = 0; ++b; } }
+    }
+};
+
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
-patch_ir2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap xmap_tail,
-                 const __grid_constant__ CUtensorMap ymap, const IR2Params p) {
+patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    uint64_t* bar_x = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
-    uint64_t* bar_w1 = bar_x + 1;
-    uint64_t* bar_w23 = bar_x + 2;
-    uint64_t* bar_mma1 = bar_x + 3;                       // [M1T]
-    uint64_t* bar_mma2 = bar_mma1 + C::M1T;               // [M2T]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_x + 12);
+    // mbarriers.  "full" = data ready for the consumer, "empty" = buffer may be overwritten by the producer.
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint64_t* lo_full = bars;            // [2] body rows [0, LO_ROWS) of the x tile landed (TMA transaction bytes)
+    uint64_t* hi_full = bars + 2;        // [2] remaining body rows + B1 landed
+    uint64_t* lo_empty = bars + 4;       // [2] the body tiles of GEMM1 have read A1[s] rows [0, LO_ROWS) (tcgen05.commit)
+    uint64_t* hi_empty = bars + 6;       // [2] the last tile of GEMM1 has retired: rest of A1[s] and W1[s] are free
+    uint64_t* body_ready = bars + 8;     // [2] mirror rows written, halo warps done reading the tile (one arrive per halo lane)
+    uint64_t* halo_ready = bars + 10;    // [2] both halo columns written (one arrive per halo lane)
+    uint64_t* w23_full = bars + 12;      // [2] W2T + B2 landed
+    uint64_t* acc1_full = bars + 14;     // [2][3] GEMM1 tile t of stage s in TMEM
+    uint64_t* acc1_empty = bars + 20;    // [2] epilogue 1 has drained ACC1[s]
+    uint64_t* hid_full = bars + 22;      // [2] hidden tile written
+    uint64_t* hid_empty = bars + 24;     // [2] depthwise has consumed the hidden tile
+    uint64_t* a2_full = bars + 26;       // [2] A2[k & 1] written by the depthwise warps
+    uint64_t* a2_empty = bars + 28;      // [2] A2[k & 1] free again (GEMM2 read it, the output tile staged in it has left)
+    uint64_t* acc2_full = bars + 30;     // GEMM2 tile in TMEM
+    uint64_t* acc2_empty = bars + 31;    // epilogue 2 has drained it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
     const uint32_t sm_base = smem_u32(sm);
-    const uint32_t a1_addr = sm_base + C::OFF_A1, a2_addr = sm_base + C::OFF_A2, a2t_addr = a2_addr + C::SZ_A2S;
-    const uint32_t w1_addr = sm_base + C::OFF_W1, b2_addr = sm_base + C::OFF_W23 + C::SZ_W2T;
 
     // ---------------- one-time setup ----------------
     for (int i = tid; i < C::OFF_BAR / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    for (int n = tid; n < C::HID; n += C::THREADS) {      // ShiftB1: K-major, element (n, k = 0) = BN1 shift
-        *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_SHB1 + n * 16) = __float2bfloat16_rn(p.shift[0][n]);
-        reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_B2B)[n] = __float2bfloat16_rn(p.shift[1][n]);
+    for (int s = 0; s < 2; ++s) {
+        // constant-one channel of A1: k-group KC1, channel row 0, every M-group a tile may read (row 0 of a group's 8 rows
+        // is not touched by the swizzle); BN1 shift: row k = 8 KC1 of B1
+        for (int i = tid; i < (C::LO_ROWS + C::GPT) * (C::ROWB / 4); i += C::THREADS)
+            *reinterpret_cast<uint32_t*>(sm + C::OFF_A1 + s * C::SZ_A1 + C::KC1 * C::A1_KGS + (i / (C::ROWB / 4)) * C::GRP + (i % (C::ROWB / 4)) * 4) = 0x3F803F80u;
+        for (int n = tid; n < C::HID; n += C::THREADS)
+            *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_W1 + s * C::SZ_W1 + C::KC1 * C::B1_LBO + n * 16) = __float2bfloat16_rn(p.shift[0][n]);
+        // BN3 shift: row k = ONE2 of B2; constant-one channel ONE2 of A2 when it lives in the non-swizzled tail (else the
+        // depthwise warps write it with every row, because the output staging tile reuses the swizzled part)
+        for (int n = tid; n < C::COUT; n += C::THREADS)
+            *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_W23 + s * C::SZ_W23 + C::SZ_W2T + C::KC2 * C::B2_LBO + n * 16) = __float2bfloat16_rn(p.shift[2][n]);
+        if (C::ONE2 >= 64)
+            for (int m = tid; m < 128; m += C::THREADS)
+                *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A2 + s * C::SZ_A2 + C::SZ_A2S + ((C::ONE2 - 64) / 8) * C::A2T_LBO + m * 16) = __float2bfloat16_rn(1.f);
     }
-    for (int n = tid; n < C::COUT; n += C::THREADS)
-        *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_SHB2 + n * 16) = __float2bfloat16_rn(p.shift[2][n]);
-    for (int i = tid; i < 64; i += C::THREADS) reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_ONES)[i] = __float2bfloat16_rn(1.f);
+    for (int n = tid; n < C::HID; n += C::THREADS) reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_B2B)[n] = __float2bfloat16_rn(p.shift[1][n]);
     if (tid == 0) {
-        mbar_init(bar_x, 1);
-        mbar_init(bar_w1, 1);
-        mbar_init(bar_w23, 1);
-        for (int t = 0; t < C::M1T; ++t) mbar_init(bar_mma1 + t, 1);
-        for (int t = 0; t < C::M2T; ++t) mbar_init(bar_mma2 + t, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(lo_full + s, 1);
+            mbar_init(hi_full + s, 1);
+            mbar_init(lo_empty + s, 1);
+            mbar_init(hi_empty + s, 1);
+            mbar_init(body_ready + s, 32 * C::PRODN);
+            mbar_init(halo_ready + s, 32 * C::PRODN);
+            mbar_init(w23_full + s, 1);
+            for (int t = 0; t < 3; ++t) mbar_init(acc1_full + s * 3 + t, 1);
+            mbar_init(acc1_empty + s, 128);
+            mbar_init(hid_full + s, 128);
+            mbar_init(hid_empty + s, 32 * C::DWN);
+            mbar_init(a2_full + s, 32 * C::WPH);
+            mbar_init(a2_empty + s, 1);
+        }
+        mbar_init(acc2_full, 1);
+        mbar_init(acc2_empty, 128);
         mbar_fence_init();
-        tma_prefetch_desc(&xmap);
-        tma_prefetch_desc(&xmap_tail);
-        tma_prefetch_desc(&ymap);
+        tma_prefetch_desc(&maps.lo);
+        tma_prefetch_desc(&maps.lo_tail);
+        tma_prefetch_desc(&maps.hi);
+        tma_prefetch_desc(&maps.hi_tail);
+        tma_prefetch_desc(&maps.y);
     }
-    if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    if (warp == C::W_MMA1) tmem_alloc(tmem_slot, C::TMEM_COLS);
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    const int P = p.fh * p.fw;
-    const size_t HW = (size_t)p.H * p.W;
-    // single-thread roles, elected once
-    const bool is_mma = warp == 0 && elect_one();
-    const bool is_loader = warp == C::WARPS - 1 && elect_one();
-    const bool is_storer = warp == (C::WARPS > 1 ? 1 : 0) && elect_one();
+    const int per_cta = (p.total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n0 = (int)blockIdx.x * per_cta, n1 = min(n0 + per_cta, p.total);     // this CTA's run of patches
+    PatchWalk pw;
+    pw.init(n0, p.fh, p.fw);
 
-    auto load_x_w1 = [&](int patch) {                     // loader thread: A1 and the B1 buffer are free
-        const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
-        mbar_arrive_expect_tx(bar_x, C::KC1 * C::TH * C::GRP);
+    if (warp >= C::W_PROD && warp < C::W_PROD + C::PRODN) {
+        // =============== halo warps: halo columns and mirror rows of the tile in A1[s] ===============
+        // Halo column sources (same tile rows everywhere): the left column of patch n is body column PS-1 of patch n-1,
+        // saved when that tile landed; its right column is body column 0 of patch n+1, written one iteration later, when
+        // that tile has landed; at the image border the mirror column of the own body; at the two ends of the CTA's run
+        // global memory.  All reads of the tile happen before body_ready is signalled: the body tiles of GEMM1 may then
+        // run and release rows [0, LO_ROWS) of the stage to the loader.
+        const int ptid = tid - 32 * C::W_PROD;
+        constexpr int PT = 32 * C::PRODN, NE = C::CIN * C::TH;   // NE (channel, tile row) pairs per halo column
+        const size_t HW = (size_t)p.H * p.W;
+        auto swz = [](uint32_t o) { return C::PS == 16 ? (o ^ (((o >> 7) & 1u) << 4)) : o; };
+        auto body_off = [](int e) { const int c = e % C::CIN, r = e / C::CIN; return (uint32_t)((c >> 3) * C::A1_KGS + r * C::GRP + (c & 7) * C::ROWB); };
+        auto slot_off = [&](int e, int side) {
+            const int c = e % C::CIN, r = e / C::CIN, h = side * C::TH + r;
+            return swz((uint32_t)((c >> 3) * C::A1_KGS + (C::TH + h / C::PS) * C::GRP + (c & 7) * C::ROWB + (h % C::PS) * 2));
+        };
+        // (1) what the neighbours need from a tile that has just landed: even lanes read its last column (saved: left halo of
+        //     the next patch), odd lanes its first column (right halo of the previous patch).  Channel fastest over lane
+        //     pairs, the two columns in different banks: two-way bank conflicts instead of eight-way.
+        constexpr int NT1 = (NE + PT / 2 - 1) / (PT / 2);
+        const int role = ptid & 1;
+        uint32_t t1[NT1];        // body offset | right halo slot offset << 16; 0xFFFFFFFF = no task
 #pragma unroll
-        for (int kg = 0; kg < C::KC1; ++kg) {
-            const bool tail = (C::CIN % 8 != 0) && kg == C::KC1 - 1;
-            tma_load_5d(sm + C::OFF_A1 + kg * C::A1_KGS, tail ? &xmap_tail : &xmap, pj * C::PS, 0, pi * C::PS - 1, tail ? 0 : kg, b, bar_x);
+        for (int j = 0; j < NT1; ++j) {
+            const int e = (ptid >> 1) + j * (PT / 2);
+            t1[j] = e < NE ? (body_off(e) | (slot_off(e, 1) << 16)) : 0xFFFFFFFFu;
         }
-        mbar_arrive_expect_tx(bar_w1, C::SZ_B1);
-        bulk_g2s(sm + C::OFF_W1, p.w + (size_t)patch * p.w_row_stride, C::SZ_B1, bar_w1);
-    };
-    auto load_w23 = [&](int patch) {                      // loader thread: the W2T / B2 buffer is free
-        mbar_arrive_expect_tx(bar_w23, C::SZ_W2T + C::SZ_B2);
-        bulk_g2s(sm + C::OFF_W23, p.w + (size_t)patch * p.w_row_stride + C::SZ_B1 / 2, C::SZ_W2T + C::SZ_B2, bar_w23);
-    };
-
-    // halo-column pixels: thread-constant task descriptors, the values travel in registers one patch ahead
-    uint32_t h_dst[C::NH];      // byte offset in A1 (swizzled), 0xFFFFFFFF = no task
-    int h_off[C::NH];           // element offset from the patch's (channel 0, tile row 0, body column 0), interior patches
-    uint32_t h_val[C::NH];
+        // (2) halo columns written from somewhere else (saved column, own mirror column, global memory): all lanes
+        constexpr int NT2 = (NE + PT - 1) / PT;
+        uint32_t t2[NT2];        // left slot offset | right slot offset << 16
+        uint32_t t2b[NT2];       // body offset (own mirror columns at the image border)
 #pragma unroll
-    for (int j = 0; j < C::NH; ++j) {
-        const int i = tid + j * C::THREADS;
-        h_dst[j] = 0xFFFFFFFFu;
-        h_off[j] = 0;
-        h_val[j] = 0;
-        if (i < C::HALO * C::CIN) {
-            const int c = i / C::HALO, h = i % C::HALO, side = h >= C::TH ? 1 : 0, r = h - side * C::TH;
-            uint32_t o = (c >> 3) * C::A1_KGS + (C::TH + h / C::PS) * C::GRP + (c & 7) * C::ROWB + (h % C::PS) * 2;
-            if (C::PS == 16) o ^= ((o >> 7) & 1u) << 4;
-            h_dst[j] = o;
-            h_off[j] = (int)(c * HW) + r * p.W + (side ? C::PS : -1);
+        for (int j = 0; j < NT2; ++j) {
+            const int e = ptid + j * PT;
+            t2[j] = e < NE ? (slot_off(e, 0) | (slot_off(e, 1) << 16)) : 0xFFFFFFFFu;
+            t2b[j] = e < NE ? body_off(e) : 0;
         }
-    }
-    auto prefetch_halo = [&](int patch) {
-        const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
-        const int y0 = pi * C::PS - 1, x0 = pj * C::PS;
-        const unsigned short* xb = reinterpret_cast<const unsigned short*>(p.x) + (size_t)b * C::CIN * HW;
-        const bool border = pi == 0 || pj == 0 || pi == p.fh - 1 || pj == p.fw - 1;
-        if (!border) {
-            const unsigned short* base = xb + (ptrdiff_t)y0 * p.W + x0;
+        auto own_col = [&](unsigned char* stage, int col, int side) {
 #pragma unroll
-            for (int j = 0; j < C::NH; ++j)
-                if (h_dst[j] != 0xFFFFFFFFu) h_val[j] = __ldg(base + h_off[j]);
-        } else {
+            for (int j = 0; j < NT2; ++j)
+                if (t2[j] != 0xFFFFFFFFu)
+                    *reinterpret_cast<unsigned short*>(stage + ((t2[j] >> (16 * side)) & 0xFFFFu)) =
+                        *reinterpret_cast<const unsigned short*>(stage + swz(t2b[j] + 2 * col));
+        };
+        // column gx of the image (rows reflected at the top / bottom border) -> halo slots: only at the ends of the run
+        auto copy_global = [&](const PatchWalk& w, int gx, unsigned char* stage, int side) {
+            const unsigned short* xb = reinterpret_cast<const unsigned short*>(p.x) + (size_t)w.b * C::CIN * HW;
 #pragma unroll
-            for (int j = 0; j < C::NH; ++j) {
-                const int i = tid + j * C::THREADS;
-                if (i < C::HALO * C::CIN) {
-                    const int c = i / C::HALO, h = i % C::HALO, side = h >= C::TH ? 1 : 0, r = h - side * C::TH;
-                    int gy = y0 + r, gx = side ? x0 + C::PS : x0 - 1;
+            for (int j = 0; j < NT2; ++j) {
+                const int e = ptid + j * PT;
+                if (e < NE) {
+                    const int c = e % C::CIN, r = e / C::CIN;
+                    int gy = w.pi * C::PS - 1 + r;
                     gy = gy < 0 ? -gy : (gy >= p.H ? 2 * p.H - 2 - gy : gy);
-                    gx = gx < 0 ? -gx : (gx >= p.W ? 2 * p.W - 2 - gx : gx);
-                    h_val[j] = __ldg(xb + (size_t)c * HW + (size_t)gy * p.W + gx);
+                    *reinterpret_cast<unsigned short*>(stage + ((t2[j] >> (16 * side)) & 0xFFFFu)) = __ldg(xb + (size_t)c * HW + (size_t)gy * p.W + gx);
                 }
             }
-        }
-    };
-    // registers -> A1 halo groups, mirror rows of border patches; everything the next GEMM1 needs from threads
-    auto stage_patch = [&](int patch, uint32_t par) {
+        };
+        bool prev_deferred = false;    // the right halo column of the previous patch is still to be written
+        PROF_BEGIN();
+        for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            unsigned char* a1 = sm + C::OFF_A1 + s * C::SZ_A1;
+            unsigned char* a1_prev = sm + C::OFF_A1 + (s ^ 1) * C::SZ_A1;
+            unsigned short* save = reinterpret_cast<unsigned short*>(sm + C::OFF_SAVE + s * C::SZ_SAVE);
+            const unsigned short* save_prev = reinterpret_cast<const unsigned short*>(sm + C::OFF_SAVE + (s ^ 1) * C::SZ_SAVE);
+            const int x0 = pw.pj * C::PS;
+            const bool top = pw.pi == 0, bottom = pw.pi == p.fh - 1;
+            const bool first_col = pw.pj == 0, last_col = pw.pj == p.fw - 1;
+            const bool right_next = !last_col && pw.patch + 1 < n1;
+            // the left halo column that was saved from the previous tile does not need this tile: fetch it first
+            const bool left_saved = !first_col && it > 0;
+            unsigned short lv[NT2];
+            if (left_saved) {
+                named_bar_sync(3, PT);                     // the column was saved by other lanes in the previous iteration
 #pragma unroll
-        for (int j = 0; j < C::NH; ++j)
-            if (h_dst[j] != 0xFFFFFFFFu) *reinterpret_cast<unsigned short*>(sm + C::OFF_A1 + h_dst[j]) = (unsigned short)h_val[j];
-        const int pp = patch % P, pi = pp / p.fw;
-        const bool top = pi == 0, bottom = pi == p.fh - 1;
-        if (top || bottom) {                               // tile row 0 <- row 2, row TH-1 <- row TH-3 (whole M-groups)
-            mbar_wait(bar_x, par);
-            for (int i = tid; i < C::KC1 * (C::GRP / 16); i += C::THREADS) {
-                unsigned char* base = sm + C::OFF_A1 + (i / (C::GRP / 16)) * C::A1_KGS + (i % (C::GRP / 16)) * 16;
-                if (top) *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(base + 2 * C::GRP);
-                if (bottom) *reinterpret_cast<uint4*>(base + (C::TH - 1) * C::GRP) = *reinterpret_cast<const uint4*>(base + (C::TH - 3) * C::GRP);
+                for (int j = 0; j < NT2; ++j) lv[j] = t2[j] != 0xFFFFFFFFu ? save_prev[ptid + j * PT] : (unsigned short)0;
             }
-        }
-    };
-
-    constexpr uint32_t IDESC1 = idesc_bf16_f32(128, C::N1, /*A MN-major*/ true, false);
-    constexpr uint32_t IDESC1_INIT = idesc_bf16_f32(128, C::N1, false, false);
-    constexpr uint32_t IDESC2 = idesc_bf16_f32(128, C::N2, false, false);
-    const uint64_t ones_desc = smem_desc(sm_base + C::OFF_ONES, 0, 0, SWZ_NONE);
-    // TMEM lanes 32q..32q+31 are reachable only from warps with warp % 4 == q
-    const int q = warp & 3, q_warps = (C::WARPS - q + 3) / 4, q_rank = warp >> 2;
-
-    int patch = blockIdx.x;
-    if (patch < p.total) {
-        if (is_loader) { load_x_w1(patch); load_w23(patch); }
-        prefetch_halo(patch);
-        stage_patch(patch, 0);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-
-#ifdef HSB_IR_PROF
-    long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long prof_t = clock64();
-#endif
-    uint32_t it = 0;
-    for (; patch < p.total; patch += gridDim.x, ++it) {
-        const uint32_t par = it & 1;
-        HSB_STAMP(11);
-        const int next = patch + gridDim.x;
-        const int b = patch / P, pp = patch % P, pi = pp / p.fw, pj = pp % p.fw;
-
-        // ---------------- A: GEMM1 (+ BN1 shift), loads and halo prefetch for the next patch ----------------
-        if (is_mma) {
-            mbar_wait(bar_x, par);
-            mbar_wait(bar_w1, par);
-            tc_fence_after_sync();
-#pragma unroll
-            for (int t = 0; t < C::M1T; ++t) {
-                umma_bf16(tmem + t * C::N1, ones_desc, smem_desc(sm_base + C::OFF_SHB1, C::N1 * 16, 128, SWZ_NONE), IDESC1_INIT, false);
-#pragma unroll
-                for (int s = 0; s < C::K1 / 16; ++s) {
-                    const uint32_t a = a1_addr + 2 * s * C::A1_KGS + t * C::GPT * C::A1_MGS;
-                    const uint64_t da = C::PS == 16 ? smem_desc(a, C::A1_MGS, C::A1_KGS, SWZ_32B_MODE)
-                                                    : smem_desc(a, C::A1_KGS, C::A1_MGS, SWZ_NONE);
-                    umma_bf16(tmem + t * C::N1, da, smem_desc(w1_addr + 2 * s * C::B1_LBO, C::B1_LBO, 128, SWZ_NONE), IDESC1, true);
+            PWAIT(0, lo_full + s, ph);                      // the tile has landed
+            PWAIT(1, hi_full + s, ph);
+            if (top || bottom) {                           // tile row 0 <- row 2, row TH-1 <- row TH-3 (whole M-groups)
+                for (int i = ptid; i < C::KC1 * (C::GRP / 16); i += PT) {
+                    unsigned char* base = a1 + (i / (C::GRP / 16)) * C::A1_KGS + (i % (C::GRP / 16)) * 16;
+                    if (top) *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(base + 2 * C::GRP);
+                    if (bottom) *reinterpret_cast<uint4*>(base + (C::TH - 1) * C::GRP) = *reinterpret_cast<const uint4*>(base + (C::TH - 3) * C::GRP);
                 }
-                umma_commit(bar_mma1 + t);
+                named_bar_sync(2, PT);                     // the column copies below read the mirrored rows
             }
-        }
-        if (next < p.total) {
-            if (is_loader) {
-                mbar_wait(bar_mma1 + C::M1T - 1, par);     // GEMM1 has retired: A1 and B1 may be overwritten
-                load_x_w1(next);
-            }
-            prefetch_halo(next);
-        }
-
-        HSB_STAMP(0);
-        // ---------------- B: epilogue 1, tile by tile as the MMAs retire: TMEM -> ReLU6 -> hidden tile ----------------
-        for (int t = q_rank; t < C::M1T; t += q_warps) {
-            if (t * 128 + q * 32 >= C::T) continue;
-            mbar_wait(bar_mma1 + t, par);
-            tc_fence_after_sync();
-            const int m = t * 128 + q * 32 + lane;
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + t * C::N1;
-            int hpix;                                      // position of M row m in the TH x TH hidden tile
-            if (m < C::BODY) hpix = (m / C::PS) * C::TH + (m % C::PS) + 1;
-            else { const int h = m - C::BODY, side = h >= C::TH ? 1 : 0; hpix = (h - side * C::TH) * C::TH + (side ? C::TH - 1 : 0); }
-            unsigned char* hrow = sm + C::OFF_HID + (size_t)hpix * C::HPITCH;
-            const bool live = m < C::T;
-            constexpr int FULL = C::HID / 16, REM = C::HID % 16;
+            if (role == 0 ? right_next : prev_deferred) {
+                unsigned short v[NT1];
+                const int col = role == 0 ? C::PS - 1 : 0;
 #pragma unroll
-            for (int ch = 0; ch < FULL; ch += 2) {
-                uint32_t v0[16], v1[16];
-                tmem_ld16(taddr + ch * 16, v0);
-                if (ch + 1 < FULL) tmem_ld16(taddr + (ch + 1) * 16, v1);
-                tmem_ld_wait();
-                uint32_t o[8];
+                for (int j = 0; j < NT1; ++j)
+                    v[j] = t1[j] != 0xFFFFFFFFu ? *reinterpret_cast<const unsigned short*>(a1 + swz((t1[j] & 0xFFFFu) + 2 * col)) : (unsigned short)0;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = relu6_pack(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1]));
-                if (live) {
-                    *reinterpret_cast<uint4*>(hrow + ch * 32) = make_uint4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<uint4*>(hrow + ch * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
-                }
-                if (ch + 1 < FULL) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = relu6_pack(__uint_as_float(v1[2 * e]), __uint_as_float(v1[2 * e + 1]));
-                    if (live) {
-                        *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32) = make_uint4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                for (int j = 0; j < NT1; ++j) {
+                    if (t1[j] != 0xFFFFFFFFu) {
+                        if (role == 0) save[(ptid >> 1) + j * (PT / 2)] = v[j];
+                        else *reinterpret_cast<unsigned short*>(a1_prev + (t1[j] >> 16)) = v[j];
                     }
                 }
             }
-            if (REM > 0) {
-                static_assert(REM == 0 || REM == 4 || REM == 8 || REM == 12, "hidden width must be a multiple of 4");
-                uint32_t v8[8], v4[4];
-                if (REM >= 8) tmem_ld8(taddr + FULL * 16, v8);
-                constexpr int c4 = FULL * 16 + (REM >= 8 ? 8 : 0);
-                if (REM % 8 == 4) tmem_ld4(taddr + c4, v4);
-                tmem_ld_wait();
-                if (REM >= 8) {
-                    uint32_t o[4];
+            // halo columns of this patch that do not come from the next tile
+            if (left_saved) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = relu6_pack(__uint_as_float(v8[2 * e]), __uint_as_float(v8[2 * e + 1]));
-                    if (live) *reinterpret_cast<uint4*>(hrow + FULL * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                for (int j = 0; j < NT2; ++j)
+                    if (t2[j] != 0xFFFFFFFFu) *reinterpret_cast<unsigned short*>(a1 + (t2[j] & 0xFFFFu)) = lv[j];
+            } else if (first_col) own_col(a1, 1, 0);
+            else copy_global(pw, x0 - 1, a1, 0);
+            if (last_col) own_col(a1, C::PS - 2, 1);
+            else if (!right_next) copy_global(pw, x0 + C::PS, a1, 1);
+            fence_proxy_async_smem();
+            mbar_arrive(body_ready + s);
+            if (prev_deferred) mbar_arrive(halo_ready + (s ^ 1));
+            if (!right_next) mbar_arrive(halo_ready + s);
+            prev_deferred = right_next;
+        }
+        PROF_END(0, ptid == 0);
+    } else if (warp == C::W_LOAD) {
+        // =============== loader: the x tile of patch n into stage s in two parts, each as soon as GEMM1 has released it ===============
+        PROF_BEGIN();
+        for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            unsigned char* a1 = sm + C::OFF_A1 + s * C::SZ_A1;
+            const int x0 = pw.pj * C::PS, y0 = pw.pi * C::PS - 1;
+            PWAIT(0, lo_empty + s, ph ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(lo_full + s, C::KC1 * C::LO_ROWS * C::GRP);
+#pragma unroll
+                for (int kg = 0; kg < C::KC1; ++kg) {
+                    const bool tail = (C::CIN % 8 != 0) && kg == C::KC1 - 1;
+                    tma_load_5d(a1 + kg * C::A1_KGS, tail ? &maps.lo_tail : &maps.lo, x0, 0, y0, tail ? 0 : kg, pw.b, lo_full + s);
                 }
-                if (REM % 8 == 4) {
-                    const uint32_t o0 = relu6_pack(__uint_as_float(v4[0]), __uint_as_float(v4[1]));
-                    const uint32_t o1 = relu6_pack(__uint_as_float(v4[2]), __uint_as_float(v4[3]));
-                    if (live) *reinterpret_cast<uint2*>(hrow + c4 * 2) = make_uint2(o0, o1);
+            }
+            __syncwarp();
+            PWAIT(1, hi_empty + s, ph ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(hi_full + s, C::KC1 * C::HI_ROWS * C::GRP + C::SZ_B1);
+                if (C::HI_ROWS > 0) {
+#pragma unroll
+                    for (int kg = 0; kg < C::KC1; ++kg) {
+                        const bool tail = (C::CIN % 8 != 0) && kg == C::KC1 - 1;
+                        tma_load_5d(a1 + kg * C::A1_KGS + C::LO_ROWS * C::GRP, tail ? &maps.hi_tail : &maps.hi, x0, 0, y0 + C::LO_ROWS, tail ? 0 : kg, pw.b, hi_full + s);
+                    }
+                }
+                bulk_g2s(sm + C::OFF_W1 + s * C::SZ_W1, p.w + (size_t)pw.patch * p.w_row_stride, C::SZ_B1, hi_full + s);
+            }
+            __syncwarp();
+        }
+        PROF_END(7, lane == 0);
+    } else if (warp == C::W_MMA1) {
+        // =============== GEMM1 issue: the body tiles first, the tile with the halo groups when both halo columns are there ===============
+        constexpr uint32_t IDESC1 = idesc_bf16_f32(128, C::N1, /*A MN-major*/ true, false);
+        PROF_BEGIN();
+        for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            const uint32_t a1_addr = sm_base + C::OFF_A1 + s * C::SZ_A1, w1_addr = sm_base + C::OFF_W1 + s * C::SZ_W1;
+            const uint32_t acc = tmem + s * C::ACC1_COLS;
+            auto issue_tile = [&](int t, int first_group) {
+#pragma unroll
+                for (int k = 0; k < C::K1 / 16; ++k) {
+                    const uint32_t a = a1_addr + 2 * k * C::A1_KGS + first_group * C::A1_MGS;
+                    const uint64_t da = C::PS == 16 ? smem_desc(a, C::A1_MGS, C::A1_KGS, SWZ_32B_MODE)
+                                                    : smem_desc(a, C::A1_KGS, C::A1_MGS, SWZ_NONE);
+                    umma_bf16(acc + t * C::N1, da, smem_desc(w1_addr + 2 * k * C::B1_LBO, C::B1_LBO, 128, SWZ_NONE), IDESC1, k > 0);
+                }
+                umma_commit(acc1_full + s * 3 + t);
+            };
+            PWAIT(0, lo_full + s, ph);
+            PWAIT(1, hi_full + s, ph);                      // B1 travels with the second part
+            PWAIT(2, body_ready + s, ph);
+            PWAIT(3, acc1_empty + s, ph ^ 1);
+            tc_fence_after_sync();
+            if (elect_one()) {
+#pragma unroll
+                for (int t = 0; t < C::NBT; ++t) issue_tile(t, t * C::GPT);
+                umma_commit(lo_empty + s);
+            }
+            __syncwarp();
+            PWAIT(4, halo_ready + s, ph);
+            tc_fence_after_sync();
+            if (elect_one()) {
+                issue_tile(C::NBT, C::LO_ROWS);
+                umma_commit(hi_empty + s);
+            }
+            __syncwarp();
+        }
+        PROF_END(1, lane == 0);
+    } else if (warp == C::W_MMA2) {
+        // =============== GEMM2 issue ===============
+        constexpr uint32_t IDESC2 = idesc_bf16_f32(128, C::N2, false, false);
+        uint32_t k = 0;
+        PROF_BEGIN();
+        for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            PWAIT(0, w23_full + s, ph);
+#pragma unroll 1
+            for (int half = 0; half < C::M2T; ++half, ++k) {
+                const uint32_t hb = k & 1;
+                PWAIT(1, a2_full + hb, (k >> 1) & 1);
+                PWAIT(2, acc2_empty, (k & 1) ^ 1);
+                tc_fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t a2_addr = sm_base + C::OFF_A2 + hb * C::SZ_A2, a2t_addr = a2_addr + C::SZ_A2S;
+                    const uint32_t b2_addr = sm_base + C::OFF_W23 + s * C::SZ_W23 + C::SZ_W2T;
+                    const uint32_t acc = tmem + C::ACC2_COL;
+#pragma unroll
+                    for (int q = 0; q < C::K2 / 16; ++q) {
+                        const uint64_t da = q < 4 ? smem_desc(a2_addr + q * 32, 16, 1024, SWZ_128B)
+                                                  : smem_desc(a2t_addr + 2 * (q - 4) * C::A2T_LBO, C::A2T_LBO, 128, SWZ_NONE);
+                        umma_bf16(acc, da, smem_desc(b2_addr + 2 * q * C::B2_LBO, C::B2_LBO, 128, SWZ_NONE), IDESC2, q > 0);
+                    }
+                    umma_commit(acc2_full);
+                }
+                __syncwarp();
+            }
+        }
+        PROF_END(2, lane == 0);
+    } else if (warp < C::W_EPI2) {
+        // =============== epilogue 1: ACC1[s] -> ReLU6 -> bf16 -> hidden tile HID[s]; warp = TMEM lane quadrant ===============
+        const int q = warp & 3;
+        PROF_BEGIN();
+        for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            PWAIT(0, hid_empty + s, ph ^ 1);
+            unsigned char* hid = sm + C::OFF_HID + s * C::SZ_HID;
+#pragma unroll 1
+            for (int t = 0; t < C::M1T; ++t) {
+                // M row -> pixel of the TH x TH hidden tile (-1: a row nobody needs)
+                const int ml = q * 32 + lane;
+                int hpix = -1;
+                if (t < C::NBT) {
+                    const int m = t * 128 + ml;
+                    if (m < C::LO_ROWS * C::PS) hpix = (m / C::PS) * C::TH + (m % C::PS) + 1;
+                    if (t * 128 + q * 32 >= C::LO_ROWS * C::PS) continue;
+                } else {
+                    if (ml < C::HI_ROWS * C::PS) hpix = (C::LO_ROWS + ml / C::PS) * C::TH + (ml % C::PS) + 1;
+                    else if (ml < C::HI_ROWS * C::PS + C::HALO) {
+                        const int h = ml - C::HI_ROWS * C::PS, side = h >= C::TH ? 1 : 0;
+                        hpix = (h - side * C::TH) * C::TH + (side ? C::TH - 1 : 0);
+                    }
+                    if (q * 32 >= C::HI_ROWS * C::PS + C::HALO) continue;
+                }
+                PWAIT(1 + t, acc1_full + s * 3 + t, ph);
+                tc_fence_after_sync();
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + s * C::ACC1_COLS + t * C::N1;
+                unsigned char* hrow = hid + (size_t)(hpix < 0 ? 0 : hpix) * C::HPITCH;
+                const bool live = hpix >= 0;
+                constexpr int FULL = C::HID / 16, REM = C::HID % 16;
+#pragma unroll
+                for (int ch = 0; ch < FULL; ch += 2) {
+                    uint32_t v0[16], v1[16];
+                    tmem_ld16(taddr + ch * 16, v0);
+                    if (ch + 1 < FULL) tmem_ld16(taddr + (ch + 1) * 16, v1);
+                    tmem_ld_wait();
+                    uint32_t o[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = relu6_pack(__uint_as_float(v0[2 * e]), __uint_as_float(v0[2 * e + 1]));
+                    if (live) {
+                        *reinterpret_cast<uint4*>(hrow + ch * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                        *reinterpret_cast<uint4*>(hrow + ch * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                    if (ch + 1 < FULL) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = relu6_pack(__uint_as_float(v1[2 * e]), __uint_as_float(v1[2 * e + 1]));
+                        if (live) {
+                            *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<uint4*>(hrow + (ch + 1) * 32 + 16) = make_uint4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
+                }
+                if (REM > 0) {
+                    static_assert(REM == 0 || REM == 4 || REM == 8 || REM == 12, "hidden width must be a multiple of 4");
+                    uint32_t v8[8], v4[4];
+                    if (REM >= 8) tmem_ld8(taddr + FULL * 16, v8);
+                    constexpr int c4 = FULL * 16 + (REM >= 8 ? 8 : 0);
+                    if (REM % 8 == 4) tmem_ld4(taddr + c4, v4);
+                    tmem_ld_wait();
+                    if (REM >= 8) {
+                        uint32_t o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = relu6_pack(__uint_as_float(v8[2 * e]), __uint_as_float(v8[2 * e + 1]));
+                        if (live) *reinterpret_cast<uint4*>(hrow + FULL * 32) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                    if (REM % 8 == 4) {
+                        const uint32_t o0 = relu6_pack(__uint_as_float(v4[0]), __uint_as_float(v4[1]));
+                        const uint32_t o1 = relu6_pack(__uint_as_float(v4[2]), __uint_as_float(v4[3]));
+                        if (live) *reinterpret_cast<uint2*>(hrow + c4 * 2) = make_uint2(o0, o1);
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            mbar_arrive(acc1_empty + s);
+            mbar_arrive(hid_full + s);
+        }
+        PROF_END(3, tid == 0);
+    } else if (warp < C::W_DW) {
+        // =============== epilogue 2: ACC2 -> bf16 -> staging tile [c][u][v] inside the consumed A2 -> TMA store ===============
+        const int q = warp & 3;
+        const bool is_storer = warp == C::W_EPI2 && elect_one();
+        // the storer also streams the W2T | B2 part of the weight rows: stage s is free when GEMM2 of its patch has retired
+        auto load_w23 = [&](int patch, uint32_t s) {
+            mbar_arrive_expect_tx(w23_full + s, C::SZ_W2T + C::SZ_B2);
+            bulk_g2s(sm + C::OFF_W23 + s * C::SZ_W23, p.w + (size_t)patch * p.w_row_stride + C::SZ_B1 / 2, C::SZ_W2T + C::SZ_B2, w23_full + s);
+        };
+        if (is_storer) {
+            load_w23(n0, 0);
+            if (n0 + 1 < n1) load_w23(n0 + 1, 1);
+        }
+        uint32_t k = 0;
+        PROF_BEGIN();
+        for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
+#pragma unroll 1
+            for (int half = 0; half < C::M2T; ++half, ++k) {
+                const uint32_t hb = k & 1;
+                PWAIT(0, acc2_full, k & 1);                // GEMM2 has retired: the accumulator is complete, A2[hb] has been read
+                if (is_storer && half == C::M2T - 1 && pw.patch + 2 < n1) load_w23(pw.patch + 2, it & 1);
+                tc_fence_after_sync();
+                const int pix = q * 32 + lane;              // pixel inside the half
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + C::ACC2_COL;
+                unsigned char* ydst = sm + C::OFF_A2 + hb * C::SZ_A2 + pix * 2;
+                uint32_t v[C::N2];
+#pragma unroll
+                for (int c0 = 0; c0 < C::COUT; c0 += 16) {
+                    if (C::COUT - c0 > 8) {
+                        uint32_t t16[16]; tmem_ld16(taddr + c0, t16);
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[c0 + e] = t16[e];
+                    } else if (C::COUT - c0 > 4) {
+                        uint32_t t8[8]; tmem_ld8(taddr + c0, t8);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[c0 + e] = t8[e];
+                    } else {
+                        uint32_t t4[4]; tmem_ld4(taddr + c0, t4);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[c0 + e] = t4[e];
+                    }
+                }
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                mbar_arrive(acc2_empty);                   // the next GEMM2 may overwrite the accumulator
+                if (pix < C::HALF_PX) {
+#pragma unroll
+                    for (int c = 0; c < C::COUT; ++c)
+                        *reinterpret_cast<__nv_bfloat16*>(ydst + c * C::HALF_PX * 2) = __float2bfloat16_rn(__uint_as_float(v[c]));
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (is_storer) {
+                    tma_store_4d(&maps.y, sm + C::OFF_A2 + hb * C::SZ_A2, pw.pj * C::PS, pw.pi * C::PS + half * C::RPH, 0, pw.b);
+                    bulk_commit();
+#ifdef HSB_IR_PROF
+                    const long long tw_ = clock64();
+#endif
+                    bulk_wait_read0();                     // the staging tile has been read: A2[hb] is free
+#ifdef HSB_IR_PROF
+                    prof_acc[1] += clock64() - tw_;
+#endif
+                    mbar_arrive(a2_empty + hb);
                 }
             }
         }
-        HSB_STAMP(1);
-        if (is_storer && it > 0) bulk_wait_read0();        // the previous output tile has left A2
-        tc_fence_before_sync();
-        __syncthreads();                                   // S2: hidden tile complete, accumulators drained
-        HSB_STAMP(2);
-
-        // ---------------- C/D: depthwise 3x3 + BN2 + ReLU6 -> A2, one M tile at a time; GEMM2 behind it ----------------
-        {
-            const __nv_bfloat162 six = __floats2bfloat162_rn(6.f, 6.f);
-            const bool main_thr = warp < C::DWW && (lane & 15) < C::MAINQ;
-            const bool tail_thr = C::TAILQ > 0 && warp == C::DWW && (lane >> 3) * 2 < C::RPH;
-            // main: quad = lane & 15, columns (2 warp, 2 warp + 1), rows rq*RQ ..;  tail: quad 16, columns (2 (lane & 7), +1), rows 2 (lane >> 3) ..
-            const int quad = main_thr ? (lane & 15) : 16;
-            const int v0 = main_thr ? 2 * warp : 2 * (lane & 7);
-            const int lr0 = main_thr ? (lane >> 4) * C::RQ : (lane >> 3) * 2;     // first output row inside the half
-            const int nrows = main_thr ? C::RQ : 2;
-            __nv_bfloat162 wt[9][2], bias[2];
-            if (main_thr || tail_thr) {
-                mbar_wait(bar_w23, par);
+        if (is_storer) bulk_wait0();
+        PROF_END(4, is_storer);
+    } else if (warp < C::W_PROD) {
+        // =============== depthwise 3x3 + BN2 + ReLU6: HID[s] -> A2, packed bf16x2 ===============
+        // thread = 4 channels (quad) x WT adjacent columns x RPT rows: every hidden pixel is read (RPT + 2)(WT + 2) / (RPT WT)
+        // = 3 times (8-byte shared loads); results go straight into GEMM2's A operand.
+        const int dw = warp - C::W_DW;
+        const __nv_bfloat162 six = __floats2bfloat162_rn(6.f, 6.f);
+        // half = dw / WPH (both halves of a 16x16 patch at the same time), row group = (dw % WPH) / (STRIPS / 2),
+        // quad = lane & 15, strip = 2 (dw % (STRIPS / 2)) + (lane >> 4)
+        const int quad = lane & 15;
+        const int my_half = dw / C::WPH, rg = (dw % C::WPH) / (C::STRIPS / 2);
+        const int strip = 2 * (dw % (C::STRIPS / 2)) + (lane >> 4);
+        const bool active = quad < C::MAINQ;
+        // when the constant-one channel of A2 sits in the swizzled part, the (idle) lanes of that channel quad write it
+        const bool ones_lane = C::ONE2 < 64 && quad == C::ONE2 / 4;
+        const int c0 = strip * C::WT, lr0 = rg * C::RPT;       // first column / first output row (inside the half) of the thread
+        uint32_t dst_off[C::WT];                              // byte offset of (output row lr0, column c0 + j) in the A2 tile
 #pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    const uint2 t2 = *reinterpret_cast<const uint2*>(sm + C::OFF_W23 + k * C::HID * 2 + quad * 8);
-                    wt[k][0] = *reinterpret_cast<const __nv_bfloat162*>(&t2.x);
-                    wt[k][1] = *reinterpret_cast<const __nv_bfloat162*>(&t2.y);
+        for (int j = 0; j < C::WT; ++j) {
+            const int m = lr0 * C::PS + c0 + j;               // row of the A2 tile; + PS per output row keeps m & 7
+            dst_off[j] = m * 128 + ((((quad >> 1) ^ (m & 7)) << 4) | ((quad & 1) << 3));
+        }
+        constexpr int dst_row = C::PS * 128;
+        // 17th quad: the HALF_PX pixels of a half are dealt to the half's WPH * 32 threads
+        constexpr int TPH = C::WPH * 32, TAIL_SKIP = TPH > C::HALF_PX ? TPH / C::HALF_PX : 1, TAIL_PER = TPH < C::HALF_PX ? C::HALF_PX / TPH : 1;
+        const int tih = (dw % C::WPH) * 32 + lane;              // thread index inside the half
+        const bool tail_lane = C::TAILQ > 0 && tih % TAIL_SKIP == 0;
+        PROF_BEGIN();
+        for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
+            const uint32_t s = it & 1, ph = (it >> 1) & 1;
+            // A2 buffer of this thread's half: buffer = half for two halves per patch, else it alternates with the patch
+            const uint32_t kk = C::M2T == 2 ? 2 * it + my_half : it, hb = kk & 1;
+            const unsigned char* wbuf = sm + C::OFF_W23 + s * C::SZ_W23;
+            const unsigned char* hid = sm + C::OFF_HID + s * C::SZ_HID;
+            unsigned char* dst = sm + C::OFF_A2 + hb * C::SZ_A2;
+            PWAIT(0, w23_full + s, ph);
+            __nv_bfloat162 wt[9][2], bias[2];
+            if (active) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const uint2 t2 = *reinterpret_cast<const uint2*>(wbuf + t * C::HID * 2 + quad * 8);
+                    wt[t][0] = *reinterpret_cast<const __nv_bfloat162*>(&t2.x);
+                    wt[t][1] = *reinterpret_cast<const __nv_bfloat162*>(&t2.y);
                 }
                 const uint2 t2 = *reinterpret_cast<const uint2*>(sm + C::OFF_B2B + quad * 8);
                 bias[0] = *reinterpret_cast<const __nv_bfloat162*>(&t2.x);
                 bias[1] = *reinterpret_cast<const __nv_bfloat162*>(&t2.y);
             }
-#pragma unroll 1
-            for (int half = 0; half < C::M2T; ++half) {
-                if (main_thr || tail_thr) {
-                    const int u0 = half * C::RPH + lr0;                     // first output row = first tile row of the window
-                    const unsigned char* src = sm + C::OFF_HID + (size_t)(u0 * C::TH + v0) * C::HPITCH + quad * 8;
-                    __nv_bfloat162 r0[4][2], r1[4][2], r2[4][2];
+            PWAIT(1, hid_full + s, ph);
+            if (active) {
+                const int u0 = my_half * C::RPH + lr0;      // first output row = first tile row of the window
+                const unsigned char* src = hid + (size_t)(u0 * C::TH + c0) * C::HPITCH + quad * 8;
+                __nv_bfloat162 r0[C::WT + 2][2], r1[C::WT + 2][2], r2[C::WT + 2][2];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint2 a = *reinterpret_cast<const uint2*>(src + j * C::HPITCH);
-                        const uint2 c = *reinterpret_cast<const uint2*>(src + (C::TH + j) * C::HPITCH);
-                        r0[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&a.x); r0[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
-                        r1[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&c.x); r1[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&c.y);
+                for (int j = 0; j < C::WT + 2; ++j) {
+                    const uint2 a = *reinterpret_cast<const uint2*>(src + j * C::HPITCH);
+                    const uint2 c = *reinterpret_cast<const uint2*>(src + (C::TH + j) * C::HPITCH);
+                    r0[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&a.x); r0[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
+                    r1[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&c.x); r1[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&c.y);
+                }
+                PWAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1);       // GEMM2 and the output store of the previous use are done with A2[hb]
+#pragma unroll
+                for (int u = 0; u < C::RPT; ++u) {
+#pragma unroll
+                    for (int j = 0; j < C::WT + 2; ++j) {
+                        const uint2 a = *reinterpret_cast<const uint2*>(src + ((u + 2) * C::TH + j) * C::HPITCH);
+                        r2[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&a.x); r2[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
                     }
-                    if (half > 0) mbar_wait(bar_mma2 + half - 1, par);     // GEMM2 of the previous half has read A2
-                    unsigned char* dst;
-                    {
-                        const int m = lr0 * C::PS + v0;                     // row of the A2 tile; m & 7 == v0 & 7 for every row step
-                        if (main_thr) dst = sm + C::OFF_A2 + m * 128 + ((((quad >> 1) ^ (m & 7)) << 4) | ((quad & 1) << 3));
-                        else dst = sm + C::OFF_A2 + C::SZ_A2S + m * 16;
-                    }
-                    // the second column's row m+1: same 128-byte-row arithmetic with (m + 1) & 7
-                    const int m1x = ((lr0 * C::PS + v0 + 1) & 7);
-                    const int dst1_delta = main_thr ? 128 + ((((quad >> 1) ^ m1x) << 4) - (((quad >> 1) ^ ((lr0 * C::PS + v0) & 7)) << 4)) : 16;
 #pragma unroll
-                    for (int u = 0; u < C::RQ; ++u) {
-                        if (u < nrows) {
+                    for (int j = 0; j < C::WT; ++j) {
+                        uint32_t o[2];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint2 a = *reinterpret_cast<const uint2*>(src + ((u + 2) * C::TH + j) * C::HPITCH);
-                                r2[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&a.x); r2[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
+                        for (int e = 0; e < 2; ++e) {
+                            __nv_bfloat162 acc = bias[e];
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                acc = __hfma2(wt[kx][e], r0[j + kx][e], acc);
+                                acc = __hfma2(wt[3 + kx][e], r1[j + kx][e], acc);
                             }
-                            uint32_t outa[2], outb[2];
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                __nv_bfloat162 pa = bias[e], pb = bias[e];
-#pragma unroll
-                                for (int kx = 0; kx < 3; ++kx) {
-                                    pa = __hfma2(wt[kx][e], r0[kx][e], pa);         pb = __hfma2(wt[kx][e], r0[kx + 1][e], pb);
-                                    pa = __hfma2(wt[3 + kx][e], r1[kx][e], pa);     pb = __hfma2(wt[3 + kx][e], r1[kx + 1][e], pb);
-                                }
-                                pa = __hfma2(wt[6][e], r2[0][e], pa);               pb = __hfma2(wt[6][e], r2[1][e], pb);
-                                pa = __hfma2(wt[7][e], r2[1][e], pa);               pb = __hfma2(wt[7][e], r2[2][e], pb);
-                                pa = __hfma2_relu(wt[8][e], r2[2][e], pa);          pb = __hfma2_relu(wt[8][e], r2[3][e], pb);
-                                pa = __hmin2(pa, six);
-                                pb = __hmin2(pb, six);
-                                outa[e] = *reinterpret_cast<uint32_t*>(&pa);
-                                outb[e] = *reinterpret_cast<uint32_t*>(&pb);
-                            }
-                            unsigned char* d = dst + u * C::PS * (main_thr ? 128 : 16);
-                            *reinterpret_cast<uint2*>(d) = make_uint2(outa[0], outa[1]);
-                            *reinterpret_cast<uint2*>(d + dst1_delta) = make_uint2(outb[0], outb[1]);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { r0[j][0] = r1[j][0]; r0[j][1] = r1[j][1]; r1[j][0] = r2[j][0]; r1[j][1] = r2[j][1]; }
+                            acc = __hfma2(wt[6][e], r2[j][e], acc);
+                            acc = __hfma2(wt[7][e], r2[j + 1][e], acc);
+                            acc = __hmin2(__hfma2_relu(wt[8][e], r2[j + 2][e], acc), six);
+                            o[e] = *reinterpret_cast<uint32_t*>(&acc);
                         }
+                        *reinterpret_cast<uint2*>(dst + dst_off[j] + u * dst_row) = make_uint2(o[0], o[1]);
                     }
-                } else if (half > 0) {
-                    mbar_wait(bar_mma2 + half - 1, par);
-                }
-                HSB_STAMP(3 + 2 * half);
-                fence_proxy_async_smem();
-                tc_fence_before_sync();
-                __syncthreads();                           // S3: this half of A2 is complete
-                HSB_STAMP(4 + 2 * half);
-                if (is_mma) {
-                    tc_fence_after_sync();
-                    umma_bf16(tmem + half * C::N2, ones_desc, smem_desc(sm_base + C::OFF_SHB2, C::N2 * 16, 128, SWZ_NONE), IDESC2, false);
 #pragma unroll
-                    for (int s = 0; s < C::K2 / 16; ++s) {
-                        const uint64_t da = s < 4 ? smem_desc(a2_addr + s * 32, 16, 1024, SWZ_128B)
-                                                  : smem_desc(a2t_addr + 2 * (s - 4) * C::A2T_LBO, C::A2T_LBO, 128, SWZ_NONE);
-                        umma_bf16(tmem + half * C::N2, da, smem_desc(b2_addr + 2 * s * C::B2_LBO, C::B2_LBO, 128, SWZ_NONE), IDESC2, true);
+                    for (int j = 0; j < C::WT + 2; ++j) { r0[j][0] = r1[j][0]; r0[j][1] = r1[j][1]; r1[j][0] = r2[j][0]; r1[j][1] = r2[j][1]; }
+                }
+            } else if (ones_lane) {
+                PWAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1);
+#pragma unroll
+                for (int u = 0; u < C::RPT; ++u)
+#pragma unroll
+                    for (int j = 0; j < C::WT; ++j) *reinterpret_cast<uint2*>(dst + dst_off[j] + u * dst_row) = make_uint2(0x00003F80u, 0u);
+            }
+            if (tail_lane) {                                // pixels of channels 64..67 (quad 16): weights are broadcast loads
+                if (!active && !ones_lane) PWAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1);
+#pragma unroll 1
+                for (int k = 0; k < TAIL_PER; ++k) {
+                    const int tail_t = tih / TAIL_SKIP + k * (TPH / TAIL_SKIP);
+                    const int tu = tail_t / C::PS, tv = tail_t % C::PS;
+                    const unsigned char* src = hid + (size_t)((my_half * C::RPH + tu) * C::TH + tv) * C::HPITCH + 16 * 8;
+                    const uint2 bq = *reinterpret_cast<const uint2*>(sm + C::OFF_B2B + 16 * 8);
+                    __nv_bfloat162 acc[2] = {*reinterpret_cast<const __nv_bfloat162*>(&bq.x), *reinterpret_cast<const __nv_bfloat162*>(&bq.y)};
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const uint2 wv = *reinterpret_cast<const uint2*>(wbuf + t * C::HID * 2 + 16 * 8);
+                        const uint2 hv = *reinterpret_cast<const uint2*>(src + ((t / 3) * C::TH + (t % 3)) * C::HPITCH);
+                        acc[0] = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&wv.x), *reinterpret_cast<const __nv_bfloat162*>(&hv.x), acc[0]);
+                        acc[1] = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&wv.y), *reinterpret_cast<const __nv_bfloat162*>(&hv.y), acc[1]);
                     }
-                    umma_commit(bar_mma2 + half);
+                    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+                    acc[0] = __hmin2(__hmax2(acc[0], zero), six);
+                    acc[1] = __hmin2(__hmax2(acc[1], zero), six);
+                    *reinterpret_cast<uint2*>(dst + C::SZ_A2S + tail_t * 16) = make_uint2(*reinterpret_cast<uint32_t*>(&acc[0]), *reinterpret_cast<uint32_t*>(&acc[1]));
                 }
             }
+            __syncwarp();                                   // idle lanes must not run ahead and arrive twice in one phase
+            fence_proxy_async_smem();
+            mbar_arrive(a2_full + hb);
+            mbar_arrive(hid_empty + s);
         }
-
-        // ---------------- E: epilogue 2: TMEM -> bf16 -> output staging tile [c][u][v] (inside A2) ----------------
-        for (int t = q_rank; t < C::M2T; t += q_warps) {
-            if (t * 128 + q * 32 >= C::OUT_PX) continue;
-            mbar_wait(bar_mma2 + C::M2T - 1, par);           // every GEMM2 tile has retired: A2 is free
-            tc_fence_after_sync();
-            const int pix = t * 128 + q * 32 + lane;
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + t * C::N2;
-            unsigned char* ydst = sm + C::OFF_A2 + pix * 2;
-#pragma unroll
-            for (int c0 = 0; c0 < C::COUT; c0 += 16) {
-                uint32_t v[16];
-                if (C::COUT - c0 > 8) tmem_ld16(taddr + c0, v);
-                else if (C::COUT - c0 > 4) { uint32_t v8[8]; tmem_ld8(taddr + c0, v8);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = v8[e]; }
-                else { uint32_t v4[4]; tmem_ld4(taddr + c0, v4);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) v[e] = v4[e]; }
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    if (c0 + e < C::COUT && pix < C::OUT_PX)
-                        *reinterpret_cast<__nv_bfloat16*>(ydst + (c0 + e) * C::OUT_PX * 2) = __float2bfloat16_rn(__uint_as_float(v[e]));
-            }
-        }
-
-        HSB_STAMP(7);
-        // ---------------- F: stage the next patch (halo pixels, mirror rows), request its W2T / B2 ----------------
-        if (next < p.total) {
-            if (is_loader) {
-                mbar_wait(bar_mma2 + C::M2T - 1, par);
-                load_w23(next);
-            }
-            stage_patch(next, par ^ 1);
-        }
-        HSB_STAMP(8);
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();                                   // S41: output tile staged, TMEM drained, A1 halo groups written
-        HSB_STAMP(9);
-        if (is_storer) {
-            tma_store_4d(&ymap, sm + C::OFF_A2, pj * C::PS, pi * C::PS, 0, b);
-            bulk_commit();
-        }
+        PROF_END(5, dw == 0 && lane == 0);
+        PROF_END(6, dw == C::DWN - 1 && lane == 0);
     }
-#ifdef HSB_IR_PROF
-    if (tid == 0) {
-        for (int k = 0; k < 12; ++k) p.prof[(size_t)blockIdx.x * 16 + k] = prof_acc[k];
-        p.prof[(size_t)blockIdx.x * 16 + 12] = it;
-    }
-#endif
-    if (is_storer) bulk_wait0();
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, C::TMEM_COLS);
+    if (warp == C::W_MMA1) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 // ---- raw -> arranged rows (for weights that were not produced by the arranged head) -----------------------------------
@@ -574,73 +800,79 @@ template <class C>
 static int launch_ir2(const void* x, void* y, const IR2Params& p, cudaStream_t st) {
     EncodeTiledFn2 encode = encode_fn();
     if (!encode) return fail(HSB_ERR_CUDA, "patch_ir2: cuTensorMapEncodeTiled is not available from the driver");
-    CUtensorMap xm, xt, ym;
+    IR2Maps maps;
     const cuuint64_t HW2 = (cuuint64_t)p.H * p.W * 2;
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const cuuint32_t box[5] = {(cuuint32_t)C::PS, 8, (cuuint32_t)C::TH, 1, 1};
     const CUtensorMapSwizzle swz = C::PS == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     const cuuint64_t xstr[4] = {HW2, (cuuint64_t)p.W * 2, 8 * HW2, (cuuint64_t)C::CIN * HW2};
-    const cuuint64_t xdim[5] = {(cuuint64_t)p.W, 8, (cuuint64_t)p.H, (cuuint64_t)(C::CIN / 8 > 0 ? C::CIN / 8 : 1), (cuuint64_t)p.B};
     CUresult r = CUDA_SUCCESS;
-    if (C::CIN >= 8)
-        r = encode(&xm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), xdim, xstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r == CUDA_SUCCESS && C::CIN % 8 != 0) {
-        const cuuint64_t tdim[5] = {(cuuint64_t)p.W, (cuuint64_t)(C::CIN % 8), (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
-        void* base = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)(C::CIN / 8) * 8 * p.H * p.W);
-        r = encode(&xt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, tdim, xstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (C::CIN < 8) xm = xt;
-    } else {
-        xt = xm;
-    }
+    // 5-D view of NCHW x: {W, c % 8, H, c / 8, B}; one box = PS pixels x 8 channels x `rows` tile rows of one channel group
+    auto make_x = [&](CUtensorMap* full, CUtensorMap* tail, int rows) {
+        const cuuint32_t box[5] = {(cuuint32_t)C::PS, 8, (cuuint32_t)rows, 1, 1};
+        if (C::CIN >= 8 && r == CUDA_SUCCESS) {
+            const cuuint64_t dim[5] = {(cuuint64_t)p.W, 8, (cuuint64_t)p.H, (cuuint64_t)(C::CIN / 8), (cuuint64_t)p.B};
+            r = encode(full, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dim, xstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        if (C::CIN % 8 != 0 && r == CUDA_SUCCESS) {   // the last, partial channel group: channels past Cin are zero fill
+            const cuuint64_t dim[5] = {(cuuint64_t)p.W, (cuuint64_t)(C::CIN % 8), (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
+            void* base = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)(C::CIN / 8) * 8 * p.H * p.W);
+            r = encode(tail, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dim, xstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (C::CIN < 8) *full = *tail;
+        } else {
+            *tail = *full;
+        }
+    };
+    make_x(&maps.lo, &maps.lo_tail, C::LO_ROWS);
+    make_x(&maps.hi, &maps.hi_tail, C::HI_ROWS > 0 ? C::HI_ROWS : 1);
     if (r == CUDA_SUCCESS) {
         const cuuint64_t ydim[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)C::COUT, (cuuint64_t)p.B};
         const cuuint64_t ystr[3] = {(cuuint64_t)p.W * 2, HW2, (cuuint64_t)C::COUT * HW2};
-        const cuuint32_t ybox[4] = {(cuuint32_t)C::PS, (cuuint32_t)C::PS, (cuuint32_t)C::COUT, 1};
-        r = encode(&ym, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, ydim, ystr, ybox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        const cuuint32_t ybox[4] = {(cuuint32_t)C::PS, (cuuint32_t)C::RPH, (cuuint32_t)C::COUT, 1};   // one half per store
+        r = encode(&maps.y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, ydim, ystr, ybox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) return fail(HSB_ERR_CUDA, "patch_ir2: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     auto kern = patch_ir2_kernel<C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("patch_ir2 attr: ") + cudaGetErrorString(e));
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    static const int force_ctas = [] { const char* v = getenv("HSB_IR_CTAS"); return v ? atoi(v) : 0; }();
-    const int ctas = force_ctas > 0 ? force_ctas : C::CTAS;
     static const bool verbose = [] { const char* v = getenv("HSB_VERBOSE"); return v && v[0] == '1'; }();
-    if (verbose) {
-        int resident = -1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, C::THREADS, (size_t)C::SMEM_BYTES);
-        fprintf(stderr, "[hsb] patch_ir2<%d,%d,%d,%d>: %d threads, %d B smem, %d TMEM cols, occupancy %d, launching %d CTAs/SM\n", C::CIN,
-                C::HID, C::COUT, C::PS, C::THREADS, C::SMEM_BYTES, C::TMEM_COLS, resident, ctas);
-        cudaGetLastError();
-    }
-    const int grid = std::min(p.total, std::max(1, device_sm_count()) * ctas);
+    if (verbose)
+        fprintf(stderr, "[hsb] patch_ir2<%d,%d,%d,%d>: %d threads, %d B smem, %d TMEM cols, one CTA per SM\n", C::CIN, C::HID, C::COUT, C::PS,
+                C::THREADS, C::SMEM_BYTES, C::TMEM_COLS);
+    const int grid = std::min(p.total, std::max(1, device_sm_count()));
 #ifdef HSB_IR_PROF
-    {   // profiling build: per-phase cycle sums of thread 0 of every CTA, printed after a synchronising launch
+    {   // profiling build: per-role wait cycles of one lane per role and CTA, printed after a synchronising launch
         static long long* dprof = nullptr;
-        if (!dprof) cudaMalloc(&dprof, 4096 * 16 * sizeof(long long));
-        cudaMemsetAsync(dprof, 0, 4096 * 16 * sizeof(long long), st);
+        if (!dprof) cudaMalloc(&dprof, 1024 * 64 * sizeof(long long));
+        cudaMemsetAsync(dprof, 0, 1024 * 64 * sizeof(long long), st);
         IR2Params pp = p;
         pp.prof = dprof;
-        kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(xm, xt, ym, pp);
+        kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(maps, pp);
         cudaStreamSynchronize(st);
-        static long long host[4096 * 16];
-        cudaMemcpy(host, dprof, sizeof(long long) * grid * 16, cudaMemcpyDeviceToHost);
-        double sum[12] = {0}; double patches = 0;
-        for (int g = 0; g < grid; ++g) { for (int k = 0; k < 12; ++k) sum[k] += (double)host[g * 16 + k]; patches += (double)host[g * 16 + 12]; }
-        static const char* names[12] = {"A issue GEMM1+prefetch", "B epilogue 1", "S2 barrier", "C depthwise half 0", "S3a barrier", "D depthwise half 1",
-                                        "S3b barrier", "E epilogue 2", "F stage next", "S41 barrier", "-", "store issue/loop"};
-        double tot = 0; for (int k = 0; k < 12; ++k) tot += sum[k];
-        fprintf(stderr, "[hsb-prof] patch_ir2<%d,%d,%d,%d> grid %d, %.0f patches, %.0f cycles/patch (thread 0)\n", C::CIN, C::HID, C::COUT, C::PS,
-                grid, patches, tot / patches);
-        for (int k = 0; k < 12; ++k) fprintf(stderr, "[hsb-prof]   %-24s %8.0f cycles/patch  %5.1f %%\n", names[k], sum[k] / patches, 100.0 * sum[k] / tot);
+        static long long host[1024 * 64];
+        cudaMemcpy(host, dprof, sizeof(long long) * grid * 64, cudaMemcpyDeviceToHost);
+        static const char* roles[8] = {"halo warps (lane 0)", "MMA1", "MMA2", "epilogue 1 (warp 0)", "epilogue 2 (storer)", "depthwise warp 0", "depthwise last warp", "loader"};
+        static const char* waits[8][7] = {{"lo_full", "hi_full", "", "", "", "", ""}, {"lo_full", "hi_full", "body_ready", "acc1_empty", "halo_ready", "", ""},
+                                          {"w23_full", "a2_full", "acc2_empty", "", "", "", ""}, {"hid_empty", "acc1_full[0]", "acc1_full[1]", "acc1_full[2]", "", "", ""},
+                                          {"acc2_full", "store read", "", "", "", "", ""}, {"w23_full", "hid_full", "a2_empty", "", "", "", ""},
+                                          {"w23_full", "hid_full", "a2_empty", "", "", "", ""}, {"lo_empty", "hi_empty", "", "", "", "", ""}};
+        const double patches = (double)p.total / grid;
+        fprintf(stderr, "[hsb-prof] patch_ir2<%d,%d,%d,%d> grid %d, %.1f patches per CTA\n", C::CIN, C::HID, C::COUT, C::PS, grid, patches);
+        for (int rr = 0; rr < 8; ++rr) {
+            double tot = 0, w[7] = {0};
+            for (int g = 0; g < grid; ++g) { tot += (double)host[(g * 8 + rr) * 8 + 7]; for (int k = 0; k < 7; ++k) w[k] += (double)host[(g * 8 + rr) * 8 + k]; }
+            double waited = 0; for (int k = 0; k < 7; ++k) waited += w[k];
+            fprintf(stderr, "[hsb-prof]  %-24s loop %7.0f cycles/patch, busy %6.0f |", roles[rr], tot / grid / patches, (tot - waited) / grid / patches);
+            for (int k = 0; k < 7; ++k) if (waits[rr][k][0]) fprintf(stderr, " %s %.0f", waits[rr][k], w[k] / grid / patches);
+            fprintf(stderr, "\n");
+        }
         note_kernel("patch_ir2_kernel");
         return check_launch("patch_ir2 launch");
     }
 #endif
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(xm, xt, ym, p);
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(maps, p);
     note_kernel("patch_ir2_kernel");
     return check_launch("patch_ir2 launch");
 }

@@ -77,3 +77,11 @@ for ln, v in sorted(per.items(), key=lambda kv: -kv[1][1])[:40]:
     st = " ".join(f"{k} {c}" for k, c in sorted(v[3].items(), key=lambda kv: -kv[1])[:4] if c)
     wf = f" smem wavefronts {v[4][0] / units:.0f} (ideal {v[4][1] / units:.0f})" if v[4][0] else ""
     print(f"line {ln:5d}: samples {100 * v[1] / max(tot_s, 1):4.1f} %  instr/unit {v[0] / units:7.1f} | {st}{wf}")
+
+print("\n--- lines by shared-memory wavefronts ---")
+tot_w = sum(v[4][0] for v in per.values())
+print(f"total {tot_w / units:.0f} wavefronts per unit (ideal {sum(v[4][1] for v in per.values()) / units:.0f})")
+for ln, v in sorted(per.items(), key=lambda kv: -kv[1][4][0])[:25]:
+    if v[4][0]:
+        ops = " ".join(f"{k} {c / units:.0f}" for k, c in sorted(v[2].items(), key=lambda kv: -kv[1])[:3])
+        print(f"line {ln:5d}: {v[4][0] / units:7.0f} wavefronts (ideal {v[4][1] / units:6.0f})  | {ops}")
