@@ -46,6 +46,11 @@ SIGNATURES = {
     "hsb_head_pack": [c_void_p, c_void_p, _F, c_int, c_int, c_int, c_int, c_void_p],
     "hsb_signal2weights_packed_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int64, c_int64, c_int64, c_void_p],
+    "hsb_head_arranged_plan": [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int64), POINTER(c_int), POINTER(c_int)],
+    "hsb_head_pack_arranged": [c_void_p, c_void_p, c_void_p, _F, _F, _F, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_int, c_int, c_int, c_void_p],
+    "hsb_signal2weights_arranged_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_int, c_int64, c_int64, c_int64, c_void_p],
     "hsb_patch_conv_fwd": [c_void_p, c_void_p, c_void_p, _F, _F, c_int,
                            c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                            c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -11,10 +11,20 @@
 //     units of 8 positions -- no transposition), streams the packed B tile (2-stage operand ring) and issues
 //     128x256xK MMAs into a 2-stage TMEM accumulator; eight epilogue warps drain TMEM -> bf16 -> a shared staging
 //     tile -> coalesced row stores, one item behind the MMAs.
+//
+// The same kernel also emits "arranged" rows for the fused inverted-residual MetaBlock (ir_arranged.cuh): the static
+// weights are then packed in the block's operand order (hsb_head_pack_arranged), which interleaves the head's groups
+// inside a tile -- an item carries its own range of signal channels (all groups its columns use, zero blocks where a
+// column belongs to another group) and the BatchNorm scales of the block are folded into the packed rows.
+#include <vector>
+
 #include "common.cuh"
+#include "ir_arranged.cuh"
 #include "tcgen05.cuh"
 
 namespace hsb {
+
+void note_kernel(const char* name);
 
 constexpr int HD_NT = 256;                 // output channels per tile
 constexpr int HD_M = 128;                  // positions per CTA
@@ -31,32 +41,43 @@ struct HeadTCParams {
     int sig_index, spg, kpad, opg, hp, groups, otiles;
     int items;                        // groups * otiles work items per position tile
     int splits;                       // CTAs sharing one position tile
+    const int4* table;                // arranged mode: per item {first signal channel, kpad, first output column, columns};
+                                      // the packed tile of item i starts at element i * nt * kpad_max
+    int kpad_max, sig_end;            // arranged mode: operand stages are sized for kpad_max; signal channels >= sig_end read as 0
     int64_t ssb, ssc;                 // signal strides (elements); position stride is 1
     int64_t row_stride;               // output row stride (elements)
 };
 
-__host__ __device__ inline size_t head_smem_bytes(int kpad) {
+__host__ __device__ inline size_t head_smem_bytes(int kpad, int nt = HD_NT) {
     size_t a = 2 * (size_t)kpad * HD_M * 2;             // two A stages (signal slab of the item's group)
-    size_t b = 2 * (size_t)HD_NT * kpad * 2;            // two B stages
-    size_t st = (size_t)HD_M * HD_STAGE_PITCH;          // output staging
+    size_t b = 2 * (size_t)nt * kpad * 2;               // two B stages
+    size_t st = (size_t)HD_M * (nt * 2 + 16);           // output staging
     return a + b + st + 128 + 1024;
+}
+
+// arranged mode: the whole signal slice of the head stays resident (one MN-major slab, k-chunks addressed per item)
+__host__ __device__ inline size_t head_smem_bytes_arranged(int sig_pad, int kpad_max, int nt) {
+    return (size_t)sig_pad * HD_M * 2 + 2 * (size_t)nt * kpad_max * 2 + (size_t)HD_M * (nt * 2 + 16) + 128 + 1024;
 }
 
 // A CTA owns 128 positions and a contiguous range of (group, channel-tile) items.  Warp 8 is the producer: it copies
 // the item's signal slab into the MN-major A operand (all 32 lanes), streams the packed B tile with cp.async.bulk and
 // issues the MMAs (lane 0) into a two-stage TMEM accumulator.  Warps 0-7 drain: quadrant = warp % 4, column half =
 // warp / 4; TMEM -> bf16 -> staging rows -> coalesced stores, one item behind the MMAs.
+template <int NT, bool ARR>
 __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const HeadTCParams p) {
+    constexpr int STAGE_PITCH = NT * 2 + 16;
     extern __shared__ unsigned char smem_dyn[];
     // align by pointer arithmetic on the __shared__ array so the compiler keeps the address space (LDS/STS, not generic)
     unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kpad = p.kpad;
-    const size_t a_bytes = (size_t)kpad * HD_M * 2, b_bytes = (size_t)HD_NT * kpad * 2;
+    const int kpad = ARR ? p.kpad_max : p.kpad;             // operand stage size; an arranged item may use less
+    // arranged mode: one resident A slab (p.kpad = padded width of the head's signal slice) instead of two stages
+    const size_t a_bytes = (size_t)(ARR ? p.kpad : kpad) * HD_M * 2, b_bytes = (size_t)NT * kpad * 2;
     unsigned char* a_sm = sm;
-    unsigned char* b_sm = a_sm + 2 * a_bytes;
+    unsigned char* b_sm = a_sm + (ARR ? 1 : 2) * a_bytes;
     unsigned char* st_sm = b_sm + 2 * b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(st_sm + (size_t)HD_M * HD_STAGE_PITCH);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(st_sm + (size_t)HD_M * STAGE_PITCH);
     uint64_t* b_full = bars;          // [2] B tile landed
     uint64_t* s_empty = bars + 2;     // [2] operand stage (A and B) consumed by the tensor core
     uint64_t* d_full = bars + 4;      // [2] accumulator ready
@@ -79,23 +100,56 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
         mbar_fence_init();
     }
     if (warp == HD_EPI_WARPS) tmem_alloc(tmem_slot, 512);
+    if (ARR) {
+        // the head's whole signal slice for these 128 positions, MN-major: unit(mc, k) = (k/8)*LBO + mc*128 + (k%8)*16 holds
+        // 8 consecutive positions of channel sig_first + k (sig_first = slice start rounded down to 8); channels outside
+        // the slice are zero (their packed weights are zero as well)
+        const int sig_first = p.sig_index & ~7, units = p.kpad * (HD_M / 8);
+        for (int base = 0; base < units; base += HD_THREADS * 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = base + e * HD_THREADS + tid;
+                const int mc = i % (HD_M / 8), k = i / (HD_M / 8), ch = sig_first + k, n = n0 + mc * 8;
+                v[e] = make_uint4(0, 0, 0, 0);
+                if (i < units && ch >= p.sig_index && ch < p.sig_end && n < p.NTOT) {
+                    const int b = n / p.P, pp = n % p.P;              // P % 8 == 0: a unit never straddles images
+                    v[e] = __ldg(reinterpret_cast<const uint4*>(p.s + (size_t)b * p.ssb + (size_t)ch * p.ssc + pp));
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = base + e * HD_THREADS + tid;
+                const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
+                if (i < units) *reinterpret_cast<uint4*>(a_sm + (k >> 3) * ((HD_M / 8) * 128) + mc * 128 + (k & 7) * 16) = v[e];
+            }
+        }
+        fence_proxy_async_smem();
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const int a_lbo = (HD_M / 8) * 128, b_lbo = (HD_NT / 8) * 128;
+    const int a_lbo = (HD_M / 8) * 128, b_lbo = (NT / 8) * 128;
 
     if (warp == HD_EPI_WARPS) {
         // ================= producer / MMA warp =================
-        const uint32_t idesc = idesc_bf16_f32(HD_M, HD_NT, /*A MN-major*/ true, false);
+        const uint32_t idesc = idesc_bf16_f32(HD_M, NT, /*A MN-major*/ true, false);
         int stage_group0 = -1, stage_group1 = -1;
-        auto stage_operands = [&](int j) {          // whole warp: A slab (if the group changed) + B tile of item j
-            const int st = j & 1, it = it0 + j, g = it / p.otiles, t = it % p.otiles;
+        auto stage_operands = [&](int j) {          // whole warp: A slab (if the signal range changed) + B tile of item j
+            const int st = j & 1, it = it0 + j;
+            int g, t, k_first, k_count, k_item;      // slab id, tile, first signal channel, channels to copy, item's padded K
+            if (ARR) {
+                const int4 e = __ldg(p.table + it);
+                g = e.x * 4096 + e.y; t = 0; k_first = e.x; k_item = e.y; k_count = max(0, min(e.y, p.sig_end - e.x));
+            } else {
+                g = it / p.otiles; t = it % p.otiles; k_first = p.sig_index + g * p.spg; k_count = p.spg; k_item = kpad;
+            }
             if (j >= 2) mbar_wait(s_empty + st, ((j >> 1) - 1) & 1);      // MMAs of item j-2 done with this stage
-            if ((st ? stage_group1 : stage_group0) != g) {
+            if (!ARR && (st ? stage_group1 : stage_group0) != g) {
                 unsigned char* a_dst = a_sm + st * a_bytes;
                 // unit(mc, k) = (k/8)*LBO + mc*128 + (k%8)*16: 8 consecutive positions of signal channel k
-                const int units = kpad * (HD_M / 8);
+                const int units = k_item * (HD_M / 8);
                 for (int base = 0; base < units; base += 32 * 8) {      // 8 independent 16-byte loads in flight per lane
                     uint4 v[8];
 #pragma unroll
@@ -104,10 +158,9 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                         const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
                         const int n = n0 + mc * 8;
                         v[e] = make_uint4(0, 0, 0, 0);
-                        if (i < units && k < p.spg && n < p.NTOT) {
+                        if (i < units && k < k_count && n < p.NTOT) {
                             const int b = n / p.P, pp = n % p.P;          // P % 8 == 0: a unit never straddles images
-                            v[e] = __ldg(reinterpret_cast<const uint4*>(p.s + (size_t)b * p.ssb +
-                                                                        (size_t)(p.sig_index + g * p.spg + k) * p.ssc + pp));
+                            v[e] = __ldg(reinterpret_cast<const uint4*>(p.s + (size_t)b * p.ssb + (size_t)(k_first + k) * p.ssc + pp));
                         }
                     }
 #pragma unroll
@@ -122,9 +175,9 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             }
             __syncwarp();
             if (elect_one()) {
-                mbar_arrive_expect_tx(b_full + st, (uint32_t)b_bytes);
-                bulk_g2s(b_sm + st * b_bytes, p.packed + ((size_t)g * p.otiles + t) * HD_NT * kpad, (uint32_t)b_bytes,
-                         b_full + st);
+                const uint32_t bytes = (uint32_t)((size_t)NT * k_item * 2);
+                mbar_arrive_expect_tx(b_full + st, bytes);
+                bulk_g2s(b_sm + st * b_bytes, p.packed + (ARR ? (size_t)it * NT * kpad : ((size_t)g * p.otiles + t) * NT * kpad), bytes, b_full + st);
             }
         };
         stage_operands(0);
@@ -135,11 +188,15 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                 mbar_wait(b_full + st, (j >> 1) & 1);
                 if (j >= 2) mbar_wait(d_empty + st, ((j >> 1) - 1) & 1);      // epilogue drained this accumulator
                 tc_fence_after_sync();
-                const uint32_t a_addr = smem_u32(a_sm + st * a_bytes), b_addr = smem_u32(b_sm + st * b_bytes);
-                for (int s = 0; s < kpad / 16; ++s) {
+                // arranged: the item's first channel (a multiple of 8 past the slab's first) selects the k-chunk of the resident slab
+                const int4 te = ARR ? __ldg(p.table + it0 + j) : make_int4(0, kpad, 0, 0);
+                const uint32_t a_addr = ARR ? smem_u32(a_sm) + ((te.x - (p.sig_index & ~7)) >> 3) * a_lbo : smem_u32(a_sm + st * a_bytes);
+                const uint32_t b_addr = smem_u32(b_sm + st * b_bytes);
+                const int ksteps = te.y / 16;
+                for (int s = 0; s < ksteps; ++s) {
                     const uint64_t da = smem_desc(a_addr + 2 * s * a_lbo, a_lbo, 128, SWZ_NONE);
                     const uint64_t db = smem_desc(b_addr + 2 * s * b_lbo, b_lbo, 128, SWZ_NONE);
-                    umma_bf16(tmem + st * HD_NT, da, db, idesc, s > 0);
+                    umma_bf16(tmem + st * NT, da, db, idesc, s > 0);
                 }
                 umma_commit(d_full + st);       // accumulator ready
                 umma_commit(s_empty + st);      // operand stage reusable
@@ -150,17 +207,24 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
         // ================= epilogue warps =================
         const int q = warp & 3, half = warp >> 2;
         const int row = q * 32 + lane;
-        constexpr int HC = HD_NT / 2;                     // columns per warp
-        unsigned char* my_row = st_sm + (size_t)row * HD_STAGE_PITCH + half * HC * 2;
+        constexpr int HC = NT / 2;                        // columns per warp
+        unsigned char* my_row = st_sm + (size_t)row * STAGE_PITCH + half * HC * 2;
         for (int j = 0; j < nitems; ++j) {
-            const int st = j & 1, it = it0 + j, g = it / p.otiles, t = it % p.otiles;
-            const int o_base = g * p.opg + t * HD_NT;
-            const int o_end = min(min((g + 1) * p.opg, p.hp), o_base + HD_NT);
+            const int st = j & 1, it = it0 + j;
+            int o_base, o_end;
+            if (ARR) {
+                const int4 e = __ldg(p.table + it);
+                o_base = e.z; o_end = e.z + e.w;
+            } else {
+                const int g = it / p.otiles, t = it % p.otiles;
+                o_base = g * p.opg + t * NT;
+                o_end = min(min((g + 1) * p.opg, p.hp), o_base + NT);
+            }
             const int nvalid = min(HC, max(o_end - o_base, 0) - half * HC);   // valid columns in this warp's half (may be <= 0)
             const int ncols = min(HC, (max(nvalid, 0) + 31) & ~31);
             mbar_wait(d_full + st, (j >> 1) & 1);
             tc_fence_after_sync();
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + st * HD_NT + half * HC;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + st * NT + half * HC;
             for (int c = 0; c < ncols; c += 32) {
                 uint32_t v0[16], v1[16];
                 tmem_ld16(taddr + c, v0);
@@ -188,7 +252,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                 const int ob = o_base + half * HC;
                 const bool pairs = (ob & 1) == 0;
                 const int nrows = min(32, p.NTOT - (n0 + q * 32));
-                const unsigned char* sbase = st_sm + (size_t)(q * 32) * HD_STAGE_PITCH + half * HC * 2;
+                const unsigned char* sbase = st_sm + (size_t)(q * 32) * STAGE_PITCH + half * HC * 2;
                 __nv_bfloat16* dbase = p.out + (size_t)(n0 + q * 32) * p.row_stride + ob;
                 if (pairs) {
                     // lane = column pair, rows unrolled: 8 independent shared loads / global stores in flight;
@@ -198,7 +262,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
 #pragma unroll 8
                         for (int r = 0; r < 32; ++r) {
                             if (r < nrows) {
-                                const unsigned char* sp = sbase + (size_t)r * HD_STAGE_PITCH + c * 2;
+                                const unsigned char* sp = sbase + (size_t)r * STAGE_PITCH + c * 2;
                                 __nv_bfloat16* dp = dbase + (size_t)r * p.row_stride + c;
                                 if (two) *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
                                 else *dp = *reinterpret_cast<const __nv_bfloat16*>(sp);
@@ -211,7 +275,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                         for (int r = 0; r < 32; ++r)
                             if (r < nrows)
                                 dbase[(size_t)r * p.row_stride + c] =
-                                    *reinterpret_cast<const __nv_bfloat16*>(sbase + (size_t)r * HD_STAGE_PITCH + c * 2);
+                                    *reinterpret_cast<const __nv_bfloat16*>(sbase + (size_t)r * STAGE_PITCH + c * 2);
                     }
                 }
             }
@@ -297,7 +361,7 @@ extern "C" int hsb_signal2weights_packed_fwd(const void* s, const void* packed, 
     p.ssb = s_stride_b; p.ssc = s_stride_c; p.row_stride = out_row_stride;
     const size_t smem = head_smem_bytes(p.kpad);
     HSB_REQUIRE(smem <= 227 * 1024, HSB_ERR_UNSUPPORTED, "signal2weights_packed: sig_ch / groups too large for one CTA");
-    cudaError_t e = cudaFuncSetAttribute(signal2weights_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(signal2weights_tc_kernel<HD_NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("signal2weights_packed attr: ") + cudaGetErrorString(e));
     p.items = groups * p.otiles;
     const int tiles = ceil_div(p.NTOT, HD_M);
@@ -313,6 +377,173 @@ extern "C" int hsb_signal2weights_packed_fwd(const void* s, const void* packed, 
     p.splits = splits;
     HSB_REQUIRE(splits <= 65535, HSB_ERR_UNSUPPORTED, "signal2weights_packed: grid too large");
     dim3 grid(tiles, splits);
-    signal2weights_tc_kernel<<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
+    p.table = nullptr; p.kpad_max = p.kpad; p.sig_end = 0;
+    signal2weights_tc_kernel<HD_NT, false><<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
+    note_kernel("signal2weights_tc_kernel");
     return check_launch("signal2weights_packed launch");
+}
+
+// ---- arranged rows for the fused inverted-residual MetaBlock -------------------------------------------------------------
+namespace hsb {
+
+constexpr int HD_NT_ARR = 128;             // arranged mode: narrower tiles keep the signal range of a tile to <= 2-3 groups
+
+struct ArrangedPlan {
+    int row_elems, items, kpad_max, sig_pad;
+    std::vector<int4> table;               // {first signal channel (relative to the head's slice), kpad, first column, columns}
+};
+
+static bool plan_arranged(int sig_index, int sig_ch, int out_ch, int groups, int hp_offset, int cin, int hid, int cout, ArrangedPlan* pl) {
+    if (sig_ch <= 0 || out_ch <= 0 || groups <= 0 || sig_ch % groups || out_ch % groups || hp_offset < 0) return false;
+    const int hp = cin * hid + 9 * hid + hid * cout;
+    if (cin <= 0 || hid <= 0 || cout <= 0 || hp_offset + hp > out_ch) return false;
+    const int spg = sig_ch / groups, opg = out_ch / groups;
+    pl->row_elems = IRRow(cin, hid, cout).bytes / 2;
+    pl->kpad_max = 16;
+    pl->table.clear();
+    // Greedy tiling of the arranged row in units of 8 columns (one 16-byte operand row: consecutive head outputs): a
+    // tile grows to 128 columns unless the next unit would widen its range of signal channels beyond what two operand
+    // stages of a CTA can hold -- that happens where the arranged order wraps around (end of one 8-channel chunk of B1,
+    // start of the next), because the head's groups are contiguous in the reference order, not in this one.
+    // the signal slice stays resident (padded: first channel rounded down to 8, + 16 so that a tile's padded range never
+    // leaves the slab); what is left of the shared memory holds two stages of packed weights
+    pl->sig_pad = ((sig_index & 7) + sig_ch + 15) / 16 * 16 + 16;
+    const long budget = 227L * 1024 - (long)pl->sig_pad * HD_M * 2 - (long)HD_M * (HD_NT_ARR * 2 + 16) - 2048;
+    const int KLIM = (int)std::min<long>(256, budget / (2 * HD_NT_ARR * 2) / 16 * 16);
+    if (KLIM < 16) return false;
+    int c0 = 0, gmin = groups, gmax = -1;
+    // channels relative to the slice; the range starts at a multiple of 8 of the absolute channel index
+    auto kfirst_of = [&](int lo) { return ((sig_index + lo * spg) & ~7) - sig_index; };
+    auto kpad_of = [&](int lo, int hi) { return hi < 0 ? 16 : ((hi + 1) * spg - kfirst_of(lo) + 15) / 16 * 16; };
+    auto flush = [&](int c1) {
+        pl->table.push_back(make_int4(gmax < 0 ? kfirst_of(0) : kfirst_of(gmin), kpad_of(gmin, gmax), c0, c1 - c0));
+        pl->kpad_max = std::max(pl->kpad_max, kpad_of(gmin, gmax));
+        c0 = c1; gmin = groups; gmax = -1;
+    };
+    for (int u = 0; u < pl->row_elems; u += 8) {
+        int ulo = groups, uhi = -1;
+        for (int e = u; e < std::min(u + 8, pl->row_elems); ++e) {
+            const IRSource src = ir_arranged_source(e, cin, hid, cout);
+            if (src.src < 0) continue;
+            const int g = (hp_offset + src.src) / opg;
+            ulo = std::min(ulo, g); uhi = std::max(uhi, g);
+        }
+        if (kpad_of(ulo, uhi) > KLIM) return false;              // one unit alone is too wide
+        const int nlo = std::min(gmin, ulo), nhi = std::max(gmax, uhi);
+        if (u > c0 && (u - c0 >= HD_NT_ARR || kpad_of(nlo, nhi) > KLIM)) flush(u);
+        gmin = std::min(gmin, ulo); gmax = std::max(gmax, uhi);
+    }
+    flush(pl->row_elems);
+    pl->items = (int)pl->table.size();
+    return true;
+}
+
+template <typename T>
+__global__ void head_pack_arranged_kernel(const T* __restrict__ ws, __nv_bfloat16* __restrict__ out, const int4* __restrict__ table,
+                                          const float* s1, const float* s2, const float* s3, int sig_index, int spg, int opg,
+                                          int hp_offset, int cin, int hid, int cout, int items, int kpad_max, int row_elems) {
+    const size_t per_item = (size_t)HD_NT_ARR * kpad_max;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < per_item * items; i += (size_t)gridDim.x * blockDim.x) {
+        const int it = (int)(i / per_item);
+        size_t r = i % per_item;
+        const int4 e = table[it];                     // kstart here is absolute (sig_index already added)
+        float v = 0.f;
+        if (r < (size_t)HD_NT_ARR * e.y) {
+            const int k8 = r % 8; r /= 8;
+            const int n8 = r % 8; r /= 8;
+            const int nc = r % (HD_NT_ARR / 8); r /= (HD_NT_ARR / 8);
+            const int kc = (int)r;
+            const int col = e.z + nc * 8 + n8;
+            if (nc * 8 + n8 < e.w && col < row_elems) {
+                const IRSource src = ir_arranged_source(col, cin, hid, cout);
+                if (src.src >= 0) {
+                    const int o = hp_offset + src.src, g = o / opg;
+                    const int k = (e.x - sig_index) + kc * 8 + k8 - g * spg;      // channel inside the group of this output (e.x may start before the slice)
+                    if (k >= 0 && k < spg) {
+                        const float sc = src.which == 0 ? s1[src.ch] : (src.which == 1 ? s2[src.ch] : s3[src.ch]);
+                        v = ld_f(ws + (size_t)o * spg + k) * sc;
+                    }
+                }
+            }
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace hsb
+
+extern "C" int hsb_head_arranged_plan(int sig_index, int sig_ch, int out_ch, int groups, int hp_offset, int Cin, int hid, int Cout,
+                                      int64_t* packed_elems, int* n_items, int* kpad_max) {
+    ArrangedPlan pl;
+    HSB_REQUIRE(plan_arranged(sig_index, sig_ch, out_ch, groups, hp_offset, Cin, hid, Cout, &pl), HSB_ERR_UNSUPPORTED,
+                "head_arranged_plan: bad dimensions, or the head's signal slice / a tile's signal range does not fit one CTA");
+    HSB_REQUIRE(head_smem_bytes_arranged(pl.sig_pad, pl.kpad_max, HD_NT_ARR) <= 227 * 1024, HSB_ERR_UNSUPPORTED,
+                "head_arranged_plan: the head's signal slice is too wide to stay resident in one CTA");
+    if (packed_elems) *packed_elems = (int64_t)pl.items * HD_NT_ARR * pl.kpad_max;
+    if (n_items) *n_items = pl.items;
+    if (kpad_max) *kpad_max = pl.kpad_max;
+    return HSB_OK;
+}
+
+extern "C" int hsb_head_pack_arranged(const void* ws, void* packed, void* table, const float* bn1_scale, const float* bn2_scale,
+                                      const float* bn3_scale, int sig_index, int sig_ch, int out_ch, int groups, int hp_offset,
+                                      int Cin, int hid, int Cout, int dtype, void* stream) {
+    HSB_REQUIRE(ws && packed && table && bn1_scale && bn2_scale && bn3_scale, HSB_ERR_INVALID_ARG, "head_pack_arranged: null pointer");
+    HSB_REQUIRE(dtype == HSB_F32 || dtype == HSB_BF16, HSB_ERR_INVALID_ARG, "head_pack_arranged: bad dtype");
+    ArrangedPlan pl;
+    HSB_REQUIRE(plan_arranged(sig_index, sig_ch, out_ch, groups, hp_offset, Cin, hid, Cout, &pl), HSB_ERR_UNSUPPORTED, "head_pack_arranged: bad dimensions");
+    for (auto& e : pl.table) e.x += sig_index;         // the kernels want absolute signal channels
+    cudaStream_t st = (cudaStream_t)stream;
+    // one-time operation: the table is tiny, a synchronous copy keeps the host vector's lifetime simple
+    cudaError_t ce = cudaMemcpyAsync(table, pl.table.data(), pl.table.size() * sizeof(int4), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("head_pack_arranged: table copy: ") + cudaGetErrorString(ce));
+    const int spg = sig_ch / groups, opg = out_ch / groups;
+    const int blocks = std::max(1, device_sm_count()) * 4;
+    if (dtype == HSB_F32)
+        head_pack_arranged_kernel<float><<<blocks, 256, 0, st>>>((const float*)ws, (__nv_bfloat16*)packed, (const int4*)table, bn1_scale, bn2_scale,
+                                                                 bn3_scale, sig_index, spg, opg, hp_offset, Cin, hid, Cout, pl.items, pl.kpad_max, pl.row_elems);
+    else
+        head_pack_arranged_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)ws, (__nv_bfloat16*)packed, (const int4*)table, bn1_scale,
+                                                                         bn2_scale, bn3_scale, sig_index, spg, opg, hp_offset, Cin, hid, Cout, pl.items,
+                                                                         pl.kpad_max, pl.row_elems);
+    return check_launch("head_pack_arranged launch");
+}
+
+extern "C" int hsb_signal2weights_arranged_fwd(const void* s, const void* packed, const void* table, void* w_arranged,
+                                               int B, int sig_index, int sig_ch, int n_items, int kpad_max, int row_elems,
+                                               int fh, int fw, int64_t s_stride_b, int64_t s_stride_c, int64_t out_row_stride,
+                                               void* stream) {
+    HSB_REQUIRE(s && packed && table && w_arranged, HSB_ERR_INVALID_ARG, "signal2weights_arranged: null pointer");
+    HSB_REQUIRE(B > 0 && sig_ch > 0 && n_items > 0 && kpad_max > 0 && kpad_max % 16 == 0 && row_elems > 0 && fh > 0 && fw > 0 && sig_index >= 0,
+                HSB_ERR_INVALID_ARG, "signal2weights_arranged: bad dimension");
+    const int P = fh * fw;
+    HSB_REQUIRE(P % 8 == 0, HSB_ERR_UNSUPPORTED, "signal2weights_arranged: fh*fw must be a multiple of 8");
+    HSB_REQUIRE(out_row_stride >= row_elems, HSB_ERR_INVALID_ARG, "signal2weights_arranged: row stride shorter than the arranged row");
+    HSB_REQUIRE(((uintptr_t)s % 16) == 0 && (s_stride_b % 8) == 0 && (s_stride_c % 8) == 0 && ((uintptr_t)packed % 16) == 0 &&
+                ((uintptr_t)table % 16) == 0, HSB_ERR_UNSUPPORTED, "signal2weights_arranged: signal / packed weights must be 16-byte aligned");
+    HeadTCParams p;
+    p.s = (const __nv_bfloat16*)s; p.packed = (const __nv_bfloat16*)packed; p.out = (__nv_bfloat16*)w_arranged;
+    const int sig_pad = ((sig_index & 7) + sig_ch + 15) / 16 * 16 + 16;
+    p.NTOT = B * P; p.P = P; p.sig_index = sig_index; p.spg = 0; p.kpad = sig_pad; p.opg = 0; p.hp = row_elems; p.groups = 1; p.otiles = n_items;
+    p.ssb = s_stride_b; p.ssc = s_stride_c; p.row_stride = out_row_stride;
+    p.table = (const int4*)table; p.kpad_max = kpad_max; p.sig_end = sig_index + sig_ch;
+    const size_t smem = head_smem_bytes_arranged(sig_pad, kpad_max, HD_NT_ARR);
+    HSB_REQUIRE(smem <= 227 * 1024, HSB_ERR_UNSUPPORTED, "signal2weights_arranged: the signal slice does not fit one CTA");
+    auto kern = signal2weights_tc_kernel<HD_NT_ARR, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("signal2weights_arranged attr: ") + cudaGetErrorString(e));
+    p.items = n_items;
+    const int tiles = ceil_div(p.NTOT, HD_M);
+    const int sms = std::max(1, device_sm_count());
+    int splits = 1, best = ceil_div(tiles, sms) * (p.items + 4);
+    for (int sp = 2; sp <= p.items; ++sp) {
+        const int cost = ceil_div(tiles * sp, sms) * (ceil_div(p.items, sp) + 4);
+        if (cost < best) { best = cost; splits = sp; }
+    }
+    p.splits = splits;
+    dim3 grid(tiles, splits);
+    kern<<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
+    note_kernel("signal2weights_tc_kernel<arranged>");
+    return check_launch("signal2weights_arranged launch");
 }

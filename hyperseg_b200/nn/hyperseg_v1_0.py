@@ -106,8 +106,52 @@ class HyperPatchInvertedResidual(nn.Module, _SignalHeadMixin):
             if not isinstance(bn, nn.BatchNorm2d):
                 raise NotImplementedError("only BatchNorm2d norm layers are fused")
 
+    def forward_arranged(self, x, s, head=None, signal_index=None, signal_channels=None, hp_offset=0):
+        """Fast inference path: the head writes this block's weights directly in the operand order of the restage-free
+        tensor-core kernel (BatchNorm scales folded into the packed head weights), and that kernel consumes them --
+        ops.signal2weights_arranged + ops.patch_ir_arranged.  ``head`` is the grouped 1x1 nn.Conv2d that generates the
+        weights (default: this layer's own ``signal2weights``); ``hp_offset`` is the first of its output channels that
+        belongs to this block (unify: one head feeds several levels).  Returns None when the path does not apply
+        (training / autograd, fp32 compute, a shape without an instantiation, residual blocks) -- the caller then takes
+        the general path."""
+        head = self.signal2weights if head is None else head
+        if head is None or self.training or self.use_res_connect or not x.is_cuda or ops._needs_grad(x, s, head.weight):
+            return None
+        if ops._compute_dtype(x) != torch.bfloat16 or not ops.head_tc_ok(s):
+            return None
+        (B, _, H, W), (fh, fw) = x.shape, s.shape[-2:]
+        if H % fh or W % fw or H // fh != W // fw or W % 8 or (H * W) % 8:
+            return None
+        if not ops.ir_arranged_supported(self.in_nc, self.hidden_dim, self.out_nc, H // fh):
+            return None
+        self._check_supported()
+        sig_index = int(self.signal_index if signal_index is None else signal_index)
+        sig_ch = int(self.signal_channels if signal_channels is None else signal_channels)
+        bns = [ops.fold_bn(bn) for bn in (self.bn1, self.bn2, self.bn3)]
+        key = (head.weight.data_ptr(), head.weight._version, head.weight.dtype, sig_index, sig_ch, int(hp_offset),
+               tuple(t.data_ptr() for pair in bns for t in pair),
+               tuple(t._version for bn in (self.bn1, self.bn2, self.bn3) for t in (bn.running_mean, bn.running_var) if t is not None))
+        cached = getattr(self, "_hsb_arranged", None)
+        if cached is None or cached[0] != key:
+            try:
+                packed = ops.ArrangedHead(head.weight, sig_index, sig_ch, head.groups, int(hp_offset), self.in_nc, self.hidden_dim,
+                                          self.out_nc, bns[0][0], bns[1][0], bns[2][0])
+            except ops._lib.HsbError:
+                packed = None                              # a tile of this head needs too wide a signal range
+            cached = (key, packed, bns)                    # keeps the folded BatchNorm tensors (and so their addresses) alive
+            self._hsb_arranged = cached
+        if cached[1] is None:
+            return None
+        w_arr = ops.signal2weights_arranged(s, cached[1])
+        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        return ops.patch_ir_arranged(xb, w_arr, self.hidden_dim, self.out_nc, bns[0][1], bns[1][1], bns[2][1])
+
     def _run(self, x, s, residual):
         self._check_supported()
+        if not residual and self.signal2weights is not None:
+            y = self.forward_arranged(x, s)
+            if y is not None:
+                return y
         weight = self.apply_signal2weights(s)
         if self.training or ops._needs_grad(x, weight):
             y = self._run_stagewise(x, weight)

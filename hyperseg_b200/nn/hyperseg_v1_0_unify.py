@@ -149,6 +149,15 @@ class MultiScaleDecoder(nn.Module):
     _coordinate_grid = staticmethod(_DecoderV10._coordinate_grid)
     get_image_coordinates = _DecoderV10.get_image_coordinates
 
+    @staticmethod
+    def _single_ir(block):
+        """The inverted-residual layer of a level that consists of nothing else (every shipped unify configuration)."""
+        if isinstance(block, HyperPatchInvertedResidual):
+            return block
+        if isinstance(block, MetaSequential) and len(block) == 1 and isinstance(block[0], HyperPatchInvertedResidual):
+            return block[0]
+        return None
+
     def forward_features(self, x, s):
         p = None
         w = None
@@ -158,12 +167,26 @@ class MultiScaleDecoder(nn.Module):
             p = assemble_level_input(coords, skip, p)
             block = self.level_blocks[level]
             if level < self.unify_level - 1:
-                p = block(p, self.weight_blocks[level](s))
+                wl = self.weight_blocks[level]
+                y = None
+                ir = self._single_ir(block)
+                if ir is not None and wl.signal2weights is not None:
+                    y = ir.forward_arranged(p, s, wl.signal2weights, wl.signal_index, wl.signal_channels)
+                p = block(p, wl(s)) if y is None else y
             else:
-                if level == self.unify_level - 1:
-                    w = self.weight_blocks[self.unify_level - 1](s)      # one head for all remaining levels
+                shared = self.weight_blocks[self.unify_level - 1]       # one head for all remaining levels
                 i = level - self.unify_level + 1
-                p = block(p, w[:, self._ranges[i]:self._ranges[i + 1]])
+                y = None
+                ir = self._single_ir(block)
+                if ir is not None and shared.signal2weights is not None:
+                    # the head writes this level's slice straight in the fused kernel's operand order
+                    y = ir.forward_arranged(p, s, shared.signal2weights, shared.signal_index, shared.signal_channels,
+                                            hp_offset=int(self._ranges[i]))
+                if y is None:
+                    if w is None:
+                        w = shared(s)
+                    y = block(p, w[:, self._ranges[i]:self._ranges[i + 1]])
+                p = y
         if self.out_fc is not None:
             p = self.out_fc(p, s)
         return p

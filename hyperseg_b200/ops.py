@@ -254,6 +254,58 @@ def patch_ir_arranged(x, w_arranged, hidden, out_channels, b1, b2, b3):
     return y
 
 
+class ArrangedHead:
+    """Static head weights of one inverted-residual block, packed in the block's operand order with its BatchNorm scales
+    folded in (hsb_head_pack_arranged).  Owned by whoever built it (the nn.Module / the engine): the buffers stay alive as
+    long as this object does, which is what a captured CUDA graph needs."""
+
+    def __init__(self, ws, sig_index, sig_ch, groups, hp_offset, cin, hidden, cout, s1, s2, s3):
+        import ctypes
+        _require_cuda(ws)
+        ws2d = ws.detach().reshape(ws.shape[0], -1)
+        if ws2d.dtype not in _DTYPES:
+            ws2d = ws2d.float()
+        ws2d = ws2d.contiguous()
+        elems, items, kmax = ctypes.c_int64(0), ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(_lib.load().hsb_head_arranged_plan(sig_index, sig_ch, ws2d.shape[0], groups, hp_offset, cin, hidden, cout,
+                                                      ctypes.byref(elems), ctypes.byref(items), ctypes.byref(kmax)), "hsb_head_arranged_plan")
+        self.sig_index, self.sig_ch, self.geom = int(sig_index), int(sig_ch), (int(cin), int(hidden), int(cout))
+        self.items, self.kpad_max, self.row = items.value, kmax.value, ir_arranged_row(cin, hidden, cout)
+        self.packed = torch.empty(elems.value, dtype=torch.bfloat16, device=ws2d.device)
+        self.table = torch.empty((self.items, 4), dtype=torch.int32, device=ws2d.device)
+        s1, _ = _affine(s1, s1, hidden, ws2d.device)
+        s2, _ = _affine(s2, s2, hidden, ws2d.device)
+        s3, _ = _affine(s3, s3, cout, ws2d.device)
+        _call("hsb_head_pack_arranged", ws2d.data_ptr(), self.packed.data_ptr(), self.table.data_ptr(), s1.data_ptr(), s2.data_ptr(),
+              s3.data_ptr(), self.sig_index, self.sig_ch, ws2d.shape[0], groups, hp_offset, cin, hidden, cout, _DTYPES[ws2d.dtype], _stream())
+
+
+def head_tc_ok(s, sig_ch_per_group=0) -> bool:
+    """True when the signal map meets the tensor-core heads' requirements (bf16 compute, 8-aligned positions)."""
+    B, C, fh, fw = s.shape
+    return s.is_cuda and _compute_dtype(s) == torch.bfloat16 and (fh * fw) % 8 == 0 and not _NO_TC_HEADS
+
+
+def signal2weights_arranged(s, head: ArrangedHead):
+    """signal (B, C, fh, fw) -> arranged rows (B, fh, fw, row) of the block ``head`` was packed for."""
+    _require_cuda(s)
+    _require_inference(s)
+    if s.dtype != torch.bfloat16:
+        s = s.to(torch.bfloat16)
+    B, C, fh, fw = s.shape
+    if head.sig_index + head.sig_ch > C:
+        raise ValueError(f"signal slice [{head.sig_index}, {head.sig_index + head.sig_ch}) exceeds {C} signal channels")
+    st = s.stride()
+    sp = st[3] if fw > 1 else (st[2] if fh > 1 else 1)
+    if sp != 1 or (fh > 1 and fw > 1 and st[2] != fw) or st[0] % 8 or st[1] % 8 or s.data_ptr() % 16:
+        s = s.contiguous()
+        st = s.stride()
+    out = torch.empty((B, fh, fw, head.row), dtype=torch.bfloat16, device=s.device)
+    _call("hsb_signal2weights_arranged_fwd", s.data_ptr(), head.packed.data_ptr(), head.table.data_ptr(), out.data_ptr(), B,
+          head.sig_index, head.sig_ch, head.items, head.kpad_max, head.row, fh, fw, st[0], st[1], head.row, _stream())
+    return out
+
+
 # (data_ptr, version, shape, groups, dtype) -> (weak reference to the weight tensor that was packed, packed bf16 operand).
 # The weak reference ties an entry to one live tensor object: a different tensor that later lands on the same address
 # (same shape, version 0) must not be served the old operand.

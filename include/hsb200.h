@@ -160,6 +160,30 @@ int hsb_signal2weights_packed_fwd(const void* s, const void* packed, void* w_out
                                   int64_t out_row_stride, void* stream);
 
 /*
+ * The weight head emitting "arranged" rows for hsb_patch_ir_arranged_fwd directly (no reference-order tensor in between):
+ * the static head weights of the block -- rows [hp_offset, hp_offset + hp) of the head, hp = Cin*hid + 9*hid + hid*Cout --
+ * are packed once in the block's operand order with its three BatchNorm scales folded in.  Because that order interleaves the
+ * head's groups, every 128-column tile carries its own range of signal channels (a small table, built by the pack call).
+ *   hsb_head_arranged_plan           sizes: bf16 elements of the packed buffer, number of tiles (= int4 table entries),
+ *                                    widest padded signal range of a tile
+ *   hsb_head_pack_arranged           ws (out_ch, sig_ch/G) -> packed + table (both caller-allocated device buffers)
+ *   hsb_signal2weights_arranged_fwd  signal -> (B, fh, fw, out_row_stride) arranged rows, row_elems =
+ *                                    hsb_ir_arranged_row_elems(Cin, hid, Cout); same signal requirements as the packed head
+ * Replaces apply_signal2weights of HyperPatchInvertedResidual (hyperseg/models/hyperseg_v1_0.py:315-326) and the slice of
+ * WeightLayer.forward that feeds an inverted-residual level (hyperseg_v1_0_unify.py:246-249, :301-309).
+ */
+int hsb_head_arranged_plan(int sig_index, int sig_ch, int out_ch, int groups, int hp_offset, int Cin, int hid, int Cout,
+                           int64_t* packed_elems, int* n_items, int* kpad_max);
+int hsb_head_pack_arranged(const void* ws, void* packed, void* table,
+                           const float* bn1_scale, const float* bn2_scale, const float* bn3_scale,
+                           int sig_index, int sig_ch, int out_ch, int groups, int hp_offset,
+                           int Cin, int hid, int Cout, int dtype, void* stream);
+int hsb_signal2weights_arranged_fwd(const void* s, const void* packed, const void* table, void* w_arranged,
+                                    int B, int sig_index, int sig_ch, int n_items, int kpad_max, int row_elems,
+                                    int fh, int fw, int64_t s_stride_b, int64_t s_stride_c, int64_t out_row_stride,
+                                    void* stream);
+
+/*
  * General patch-wise convolution (any kernel size / groups / dilation, stride 1):
  *   tile = pad(x, (pad_h,pad_w), pad_mode)[b, :, i*ph : i*ph+ph+2*pad_h, j*pw : j*pw+pw+2*pad_w]
  *   y patch = valid_conv(tile, Wm),  Wm[o,c,ky,kx] = w_patch[((o*(Cin/G)+c)*kh+ky)*kw+kx]
