@@ -74,8 +74,6 @@ SIGNATURES = {
     "hsb_bias_act_nhwc_chunks": [c_int, c_int64, c_int],
     "hsb_bias_act_nhwc_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p],
     "hsb_channel_gate_nhwc_fwd": [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p],
-    "hsb_dwconv_nhwc_chunks": [c_int, c_int, c_int, c_int],
-    "hsb_dwconv_bias_act_nhwc_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 13 + [c_void_p],
 }
 
 _INT64_RESULTS = ("hsb_head_packed_elems", "hsb_ir_arranged_row_elems")

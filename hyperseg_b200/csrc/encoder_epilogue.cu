@@ -233,138 +233,3 @@ extern "C" int hsb_channel_gate_nhwc_fwd(const void* x, const void* gate, void* 
     else channel_gate_nhwc_kernel<float><<<grid, block, 0, st>>>(p);
     return check_launch("channel_gate_nhwc launch");
 }
-
-// ---- depthwise convolution fused with its epilogue (experimental: engine flag HSB_FUSED_DW=1, not yet validated on a GPU) ----
-// y = act(dwconv_kxk(x, w) + bias[c]) on channels-last tensors, stride 1 or 2, explicit (top, left) zero padding, optional
-// per-chunk sums of the rounded output for the squeeze-and-excitation mean.  Replaces cuDNN's depthwise kernel plus the
-// bias_act pass above: the expanded activation is read once and written once.  Thread = 8 channels x a strip of P
-// output pixels along W (two, so that two CTAs fit the register file); fp32 accumulation; weights [tap][C] float in shared memory.
-namespace hsb {
-
-constexpr int DW_P = 2;       // output pixels per thread (register budget: two CTAs per SM)
-
-struct DwParams {
-    const void* x; const float* w; const float* bias; void* y; float* pool;
-    int H, W, C, Ho, Wo, pad_t, pad_l, act, G, strips_x, strips, chunks;
-};
-
-template <int K, int S>
-__global__ void __launch_bounds__(256, 2)
-dwconv_bias_act_nhwc_kernel(const DwParams p) {
-    constexpr int P = DW_P;                              // output pixels per thread
-    constexpr int IN = (P - 1) * S + K;                  // input columns a strip touches
-    extern __shared__ __align__(16) float dw_sm[];       // [K*K][C] weights | [L][C] pool partials
-    float* wsm = dw_sm;
-    float* red = dw_sm + K * K * p.C;
-    const int tid = threadIdx.x, g = tid % p.G, l = tid / p.G, L = blockDim.x / p.G;
-    const int n = blockIdx.y;
-    for (int i = tid; i < K * K * p.C; i += blockDim.x) wsm[i] = p.w[i];
-    __syncthreads();
-    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.x) + (size_t)n * p.H * p.W * p.C + g * 8;
-    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(p.y) + (size_t)n * p.Ho * p.Wo * p.C + g * 8;
-    float b[8], pool[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { b[e] = p.bias ? p.bias[g * 8 + e] : 0.f; pool[e] = 0.f; }
-    // strips of one image are dealt round-robin to (chunk, lane): fixed assignment -> deterministic partial sums
-    for (int s = blockIdx.x * L + l; s < p.strips; s += gridDim.x * L) {
-        const int oy = s / p.strips_x, ox0 = (s % p.strips_x) * P;
-        float acc[P][8];
-#pragma unroll
-        for (int q = 0; q < P; ++q)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[q][e] = b[e];
-#pragma unroll
-        for (int ky = 0; ky < K; ++ky) {
-            const int iy = oy * S - p.pad_t + ky;
-            if (iy < 0 || iy >= p.H) continue;
-            float in[IN][8];
-#pragma unroll
-            for (int j = 0; j < IN; ++j) {
-                const int ix = ox0 * S - p.pad_l + j;
-                if (ix >= 0 && ix < p.W) unpack16<__nv_bfloat16, 8>(*reinterpret_cast<const uint4*>(x + ((size_t)iy * p.W + ix) * p.C), in[j]);
-                else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) in[j][e] = 0.f;
-                }
-            }
-#pragma unroll
-            for (int kx = 0; kx < K; ++kx) {
-                const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * K + kx) * p.C + g * 8);
-                const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * K + kx) * p.C + g * 8 + 4);
-                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                for (int q = 0; q < P; ++q)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[q][e] = fmaf(wv[e], in[q * S + kx][e], acc[q][e]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < P; ++q) {
-            if (ox0 + q < p.Wo) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = epilogue_act(acc[q][e], p.act);
-                *reinterpret_cast<uint4*>(y + ((size_t)oy * p.Wo + ox0 + q) * p.C) = pack16<__nv_bfloat16, 8>(v);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) pool[e] += v[e];
-            }
-        }
-    }
-    if (p.pool) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) red[l * p.C + g * 8 + e] = pool[e];
-        __syncthreads();
-        for (int c = tid; c < p.C; c += blockDim.x) {
-            float sum = 0.f;
-            for (int i = 0; i < L; ++i) sum += red[i * p.C + c];
-            p.pool[((size_t)n * p.chunks + blockIdx.x) * p.C + c] = sum;
-        }
-    }
-}
-
-}  // namespace hsb
-
-extern "C" int hsb_dwconv_nhwc_chunks(int C, int Ho, int Wo, int stride) {
-    if (C <= 0 || C % 8 || C / 8 > 256 || Ho <= 0 || Wo <= 0 || (stride != 1 && stride != 2)) return -1;
-    const int P = DW_P, G = C / 8, L = G >= 256 ? 1 : 256 / G;
-    const int strips = Ho * ((Wo + P - 1) / P);
-    const int chunks = (strips + L - 1) / L;
-    return chunks < MAX_CHUNKS ? chunks : MAX_CHUNKS;
-}
-
-extern "C" int hsb_dwconv_bias_act_nhwc_fwd(const void* x, const float* w_taps, const float* bias, void* y, float* pool_partial,
-                                            int N, int H, int W, int C, int k, int stride, int pad_top, int pad_left,
-                                            int Ho, int Wo, int act, int dtype, void* stream) {
-    HSB_REQUIRE(x && w_taps && y, HSB_ERR_INVALID_ARG, "dwconv_nhwc: null tensor");
-    HSB_REQUIRE(dtype == HSB_BF16, HSB_ERR_UNSUPPORTED, "dwconv_nhwc: bf16 only");
-    HSB_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), HSB_ERR_UNSUPPORTED, "dwconv_nhwc: k in {3,5}, stride in {1,2}");
-    HSB_REQUIRE(act >= HSB_ACT_NONE && act <= HSB_ACT_SILU, HSB_ERR_INVALID_ARG, "dwconv_nhwc: act");
-    HSB_REQUIRE(N > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && C > 0 && C % 8 == 0 && C / 8 <= 256, HSB_ERR_UNSUPPORTED,
-                "dwconv_nhwc: C must be a multiple of 8 and at most 2048");
-    HSB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w_taps)) & 15) == 0,
-                HSB_ERR_UNSUPPORTED, "dwconv_nhwc: tensors must be 16-byte aligned");
-    DwParams p;
-    p.x = x; p.w = w_taps; p.bias = bias; p.y = y; p.pool = pool_partial;
-    p.H = H; p.W = W; p.C = C; p.Ho = Ho; p.Wo = Wo; p.pad_t = pad_top; p.pad_l = pad_left; p.act = act;
-    p.G = C / 8;
-    const int P = DW_P, L = p.G >= 256 ? 1 : 256 / p.G;
-    p.strips_x = (Wo + P - 1) / P;
-    p.strips = Ho * p.strips_x;
-    p.chunks = hsb_dwconv_nhwc_chunks(C, Ho, Wo, stride);
-    const dim3 grid(p.chunks, N), block(p.G * L);
-    const size_t smem = ((size_t)k * k * C + (pool_partial ? (size_t)L * C : 0)) * sizeof(float);
-    HSB_REQUIRE(smem <= 200 * 1024, HSB_ERR_UNSUPPORTED, "dwconv_nhwc: channel count too large");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define HSB_DW_LAUNCH(K, S)                                                                                          \
-    do {                                                                                                             \
-        auto kern = dwconv_bias_act_nhwc_kernel<K, S>;                                                               \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        kern<<<grid, block, smem, st>>>(p);                                                                          \
-    } while (0)
-    if (k == 3 && stride == 1) HSB_DW_LAUNCH(3, 1);
-    else if (k == 3) HSB_DW_LAUNCH(3, 2);
-    else if (stride == 1) HSB_DW_LAUNCH(5, 1);
-    else HSB_DW_LAUNCH(5, 2);
-#undef HSB_DW_LAUNCH
-    return check_launch("dwconv_nhwc launch");
-}

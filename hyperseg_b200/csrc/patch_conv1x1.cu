@@ -211,6 +211,7 @@ static int launch_1x1(const Conv1x1Params& p, size_t smem, cudaStream_t st) {
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         k<<<grid, 128, smem, st>>>(p);
     }
+    note_kernel("patch_conv1x1_kernel");
     return check_launch("patch_conv1x1 launch");
 }
 

@@ -189,6 +189,7 @@ extern "C" int hsb_patch_conv_fwd(const void* x, const void* w, void* y,
         if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("patch_conv attr: ") + cudaGetErrorString(e));
         patch_conv_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(p);
     }
+    note_kernel("patch_conv_kernel");
     return check_launch("patch_conv launch");
 }
 

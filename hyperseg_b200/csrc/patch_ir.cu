@@ -150,6 +150,7 @@ static int launch_ir(const IRParams& p, size_t smem, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("patch_ir attr: ") + cudaGetErrorString(e));
     k<<<p.B * p.fh * p.fw, 256, smem, st>>>(p);
+    note_kernel("patch_ir_kernel");
     return check_launch("patch_ir launch");
 }
 

@@ -1,4 +1,6 @@
-// Fused patch-wise inverted-residual MetaBlock -- bf16 tensor-core path (tcgen05 / TMEM / TMA), 16x16 and 8x8 patches.
+// Fused patch-wise inverted-residual MetaBlock -- bf16 tensor-core path (tcgen05 / TMEM / TMA), 16x16 and 8x8 patches, for
+// per-patch weights handed over in the REFERENCE order (hsb_patch_ir_fwd): this kernel re-stages them (and the x tile) into
+// UMMA operands itself.  When the weights come from our own head, the restage-free kernel in patch_ir2.cu is used instead.
 //
 // Same arithmetic as patch_ir.cu (reference hyperseg/models/hyperseg_v1_0.py:328-376), organised for sm_100a:
 //
@@ -92,13 +94,6 @@ struct IRTC {
     static constexpr int SZ_W2P = 10 * HPW * 4;
     static constexpr int OFF_BN = OFF_W2P + SZ_W2P;
     static constexpr int SZ_BN = (4 * HID + 2 * COUT) * 4;
-    // HSB_IR_X5D experiment: the x tile lands through a 5-D tensor map directly in the MN-major
-    // A1 layout.  M rows: body pixel (row r, patch column v) -> m = r*PW + v; halo-column pixels follow, left column
-    // first (m = BODY + r), then the right column (m = BODY + TH + r).
-    static constexpr int XCH = PW / 8, BODY = TH * PW, BODY_UNITS = TH * XCH, HALO = 2 * TH, HALO_UNITS = (HALO + 7) / 8;
-    static constexpr int X5_SBO = K1 * 16, X5_LBO = 128;                       // 8-pixel unit / 8-channel group strides
-    static constexpr int SZ_X5_BODY = BODY_UNITS * X5_SBO, SZ_X5_HALO = TH * X5_SBO;
-    static_assert(BODY + HALO == T && (BODY_UNITS + HALO_UNITS) * X5_SBO <= SZ_A1 && 2 * SZ_X5_HALO <= SZ_X, "x5d layout");
     static constexpr int OFF_BAR = r16(OFF_BN + SZ_BN);
     static constexpr int OFF_COORD = OFF_BAR + 64;            // int[2][4]: (b, pi, pj) of the patch in flight
     static constexpr int USED_BYTES = OFF_COORD + 32;
@@ -147,11 +142,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
-#ifdef HSB_IR_X5D
-patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap hmap, const IRTCParams p) {
-#else
 patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p) {
-#endif
     extern __shared__ unsigned char smem_dyn[];
     // align by pointer arithmetic on the __shared__ array so the compiler keeps the address space (LDS/STS, not generic)
     unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -188,9 +179,6 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         for (int t = 0; t < C::M2T; ++t) mbar_init(bar_mma2 + t, 1);
         mbar_fence_init();
         tma_prefetch_desc(&xmap);
-#ifdef HSB_IR_X5D
-        tma_prefetch_desc(&hmap);
-#endif
     }
     if (warp == 0) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before_sync();
@@ -213,18 +201,9 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         }
     };
     auto load_x = [&](uint32_t slot) {                                 // one thread, after the announcement is visible to it
-#ifdef HSB_IR_X5D
-        // body -> A1 (region Y), the two halo-column chunks -> staging in region X; chunks / rows outside the image are zero fill
-        const int cb = coord[slot * 4 + 0], cy = coord[slot * 4 + 1] * C::PH - 1, cx = coord[slot * 4 + 2] * C::XCH;
-        mbar_arrive_expect_tx(bar_tma, C::SZ_X5_BODY + 2 * C::SZ_X5_HALO);
-        tma_load_5d(sm + C::OFF_A1, &xmap, 0, 0, cx, cy, cb, bar_tma);
-        tma_load_5d(sm + C::OFF_X, &hmap, 0, 0, cx - 1, cy, cb, bar_tma);
-        tma_load_5d(sm + C::OFF_X + C::SZ_X5_HALO, &hmap, 0, 0, cx + C::XCH, cy, cb, bar_tma);
-#else
         mbar_arrive_expect_tx(bar_tma, X_BYTES);
         tma_load_4d(rawX, &xmap, coord[slot * 4 + 2] * C::PW - 8, coord[slot * 4 + 1] * C::PH - 1, 0, coord[slot * 4 + 0],
                     bar_tma);
-#endif
     };
     // in the loop an elected lane of warp 1 issues the loads while an elected lane of warp 0 issues the MMAs
     if (tid == 0 && (int)blockIdx.x < p.total) {
@@ -232,11 +211,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         load_x(0);
     }
 
-#ifdef HSB_IR_X5D
-    constexpr uint32_t IDESC1 = idesc_bf16_f32(128, C::N1, /*A MN-major*/ true, false);
-#else
     constexpr uint32_t IDESC1 = idesc_bf16_f32(128, C::N1, false, false);
-#endif
     constexpr uint32_t IDESC2 = idesc_bf16_f32(128, C::N2, false, false);
     // TMEM lanes 32q..32q+31 are only reachable from warps with warp % 4 == q: a warp serves the (tile, quadrant)
     // tasks of its own quadrant, tiles strided by the number of warps sharing that quadrant
@@ -367,40 +342,9 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         }
         // the x tile is only needed now: its flight time hid behind the weight re-stage
         if (p.w_bulk) mbar_wait(bar_tma, par);
-#ifdef HSB_IR_X5D
-        {   // the body already sits in operand layout; what is left: reflected rows, the 2*TH halo-column pixels and the
-            // constant-one channel.  Source rows of a reflection are never themselves rewritten (row 0 <- row 2), so the
-            // three steps need no barrier between them.
-            unsigned char* a1 = sm + C::OFF_A1;
-            const unsigned char* hl = sm + C::OFF_X;
-            if (top || bottom) {
-                for (int i = tid; i < C::XCH * C::CIN; i += C::THREADS) {
-                    const int ch = i / C::CIN, c = i % C::CIN;
-                    if (top) *reinterpret_cast<uint4*>(a1 + (0 * C::XCH + ch) * C::X5_SBO + c * 16) =
-                                 *reinterpret_cast<const uint4*>(a1 + (2 * C::XCH + ch) * C::X5_SBO + c * 16);
-                    if (bottom) *reinterpret_cast<uint4*>(a1 + ((C::TH - 1) * C::XCH + ch) * C::X5_SBO + c * 16) =
-                                    *reinterpret_cast<const uint4*>(a1 + ((C::TH - 3) * C::XCH + ch) * C::X5_SBO + c * 16);
-                }
-            }
-            for (int i = tid; i < C::HALO * C::CIN; i += C::THREADS) {
-                const int h = i / C::CIN, c = i % C::CIN, side = h >= C::TH ? 1 : 0, r = h - side * C::TH;
-                const int rs = (top && r == 0) ? 2 : ((bottom && r == C::TH - 1) ? C::TH - 3 : r);
-                const unsigned char* src;
-                if (side == 0) src = left ? a1 + (rs * C::XCH) * C::X5_SBO + c * 16 + 2                    // column 1 of the body
-                                          : hl + rs * C::X5_SBO + c * 16 + 14;                               // pixel 7 of the chunk to the left
-                else src = right ? a1 + (rs * C::XCH + C::XCH - 1) * C::X5_SBO + c * 16 + 12               // column PW-2
-                                 : hl + C::SZ_X5_HALO + rs * C::X5_SBO + c * 16;                             // pixel 0 of the chunk to the right
-                *reinterpret_cast<unsigned short*>(a1 + (C::BODY_UNITS + (h >> 3)) * C::X5_SBO + c * 16 + (h & 7) * 2) =
-                    *reinterpret_cast<const unsigned short*>(src);
-            }
-            for (int u = tid; u < C::BODY_UNITS + C::HALO_UNITS; u += C::THREADS)
-                *reinterpret_cast<uint4*>(a1 + u * C::X5_SBO + C::CIN * 16) = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-        }
-#else
         patch_halo();
         if (top || bottom) __syncthreads();
         restage_x();
-#endif
         fence_proxy_async_smem();          // operand writes -> visible to the tensor core (async proxy)
         tc_fence_before_sync();
         __syncthreads();
@@ -413,11 +357,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
             for (int t = 0; t < C::M1T; ++t) {
 #pragma unroll
                 for (int s = 0; s < C::K1 / 16; ++s) {
-#ifdef HSB_IR_X5D
-                    const uint64_t da = smem_desc(a1_addr + 2 * s * C::X5_LBO + t * 16 * C::X5_SBO, C::X5_LBO, C::X5_SBO, SWZ_NONE);
-#else
                     const uint64_t da = smem_desc(a1_addr + 2 * s * C::A1_LBO + t * 16 * C::A1_SBO, C::A1_LBO, C::A1_SBO, SWZ_NONE);
-#endif
                     const uint64_t db = smem_desc(b1_addr + 2 * s * C::B1_LBO, C::B1_LBO, C::B1_SBO, SWZ_NONE);
                     umma_bf16(tmem + t * C::N1, da, db, IDESC1, s > 0);
                 }
@@ -437,14 +377,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
             tc_fence_after_sync();
             const int m = t * 128 + q * 32 + lane;
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + t * C::N1;
-#ifdef HSB_IR_X5D
-            int hpix;                                     // position of M row m in the (TH x TW) hidden tile
-            if (m < C::BODY) hpix = (m / C::PW) * C::TW + (m % C::PW) + 1;
-            else { const int h = m - C::BODY, side = h >= C::TH ? 1 : 0; hpix = (h - side * C::TH) * C::TW + (side ? C::TW - 1 : 0); }
-            unsigned char* hrow = sm + C::OFF_HID + (size_t)hpix * (C::HPITCH * 2);
-#else
             unsigned char* hrow = sm + C::OFF_HID + (size_t)m * (C::HPITCH * 2);
-#endif
             constexpr int FULL = C::HID / 16, REM = C::HID % 16;
             static_assert(REM == 0 || REM == 4 || REM == 8 || REM == 12, "hidden width must be a multiple of 4");
 #pragma unroll
@@ -564,55 +497,13 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
                     for (int kx = 0; kx < 3; ++kx) { a0r[kx] = a1r[kx]; a1r[kx] = a2r[kx]; b0r[kx] = b1r[kx]; b1r[kx] = b2r[kx]; }
                 }
             };
-#ifdef HSB_IR_DW2
-            // experiment: two ADJACENT tile columns per thread -- the 3x3 windows overlap, so a
-            // row step costs 4 shared loads instead of 6 -- and one FMA chain per output (bias as the initial value)
-            auto column_adjacent = [&](int cp, int v, unsigned char* dsta, unsigned char* dstb, int dst_step) {
-                __nv_bfloat162 wt[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) wt[k] = *reinterpret_cast<const __nv_bfloat162*>(&w2p[k * C::HPW + cp]);
-                const __nv_bfloat162 bias = *reinterpret_cast<const __nv_bfloat162*>(&w2p[9 * C::HPW + cp]);
-                const uint32_t* col = hid + v * C::HPW + cp;               // hidden pixel (r, v + j) at (r*TW + v + j)*HPW
-                __nv_bfloat162 r0[4], r1[4], r2[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t t0 = col[(0 * C::TW + j) * C::HPW], t1 = col[(1 * C::TW + j) * C::HPW];
-                    r0[j] = *reinterpret_cast<__nv_bfloat162*>(&t0); r1[j] = *reinterpret_cast<__nv_bfloat162*>(&t1);
-                }
-#pragma unroll
-                for (int u = 0; u < C::PH; ++u) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t t2 = col[((u + 2) * C::TW + j) * C::HPW];
-                        r2[j] = *reinterpret_cast<__nv_bfloat162*>(&t2);
-                    }
-                    __nv_bfloat162 pa = bias, pb = bias;
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        pa = __hfma2(wt[kx], r0[kx], pa);         pb = __hfma2(wt[kx], r0[kx + 1], pb);
-                        pa = __hfma2(wt[3 + kx], r1[kx], pa);     pb = __hfma2(wt[3 + kx], r1[kx + 1], pb);
-                        pa = __hfma2(wt[6 + kx], r2[kx], pa);     pb = __hfma2(wt[6 + kx], r2[kx + 1], pb);
-                    }
-                    pa = __hmin2(__hmax2(pa, zero), six);
-                    pb = __hmin2(__hmax2(pb, zero), six);
-                    *reinterpret_cast<uint32_t*>(dsta + u * dst_step) = *reinterpret_cast<uint32_t*>(&pa);
-                    *reinterpret_cast<uint32_t*>(dstb + u * dst_step) = *reinterpret_cast<uint32_t*>(&pb);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { r0[j] = r1[j]; r1[j] = r2[j]; }
-                }
-            };
-#endif
             if (warp < C::DWW) {
                 if (lane < C::MAINP) {
                     const int cp = lane;
                     // pixel m = u*PW + v: 128-byte swizzled row m, 16-byte chunk (cp/4) ^ (m%8); m%8 == v%8 for all u
                     auto a2_dst = [&](int v) { return sm + C::OFF_A2 + v * 128 + ((((cp >> 2) ^ (v & 7)) << 4) | ((cp & 3) << 2)); };
                     if (C::PW == 2 * C::DWW) {
-#ifdef HSB_IR_DW2
-                        column_adjacent(cp, 2 * warp, a2_dst(2 * warp), a2_dst(2 * warp + 1), C::PW * 128);
-#else
                         column_pair(cp, warp, warp + C::DWW, a2_dst(warp), a2_dst(warp + C::DWW), C::PW * 128);
-#endif
                     } else {
 #pragma unroll 1
                         for (int v = warp; v < C::PW; v += C::DWW) column(cp, v, a2_dst(v), C::PW * 128);
@@ -653,9 +544,7 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
 
         // ---------------- P5: GEMM2 (accumulators reuse GEMM1's TMEM columns) ----------------
         // region X is free: the depthwise phase has consumed the hidden tile
-#ifndef HSB_IR_X5D
         if (warp == 1 && elect_one() && next < p.total) load_x(par ^ 1);
-#endif
         if (warp == 0 && elect_one()) {
             tc_fence_after_sync();
             for (int t = 0; t < C::M2T; ++t) {
@@ -672,13 +561,6 @@ patch_ir_tc_kernel(const __grid_constant__ CUtensorMap xmap, const IRTCParams p)
         }
 
         HSB_STAMP(7);
-#ifdef HSB_IR_X5D
-        // the x tile lands in region Y (A1), which GEMM2 is still reading as A2: request it once every GEMM2 tile has retired
-        if (warp == 1 && next < p.total) {
-            for (int t = 0; t < C::M2T; ++t) mbar_wait(bar_mma2 + t, par);
-            if (elect_one()) load_x(par ^ 1);
-        }
-#endif
         // ---------------- P6: epilogue 2 (TMEM -> bf16 -> NCHW) ----------------
         for (int t = q_rank; t < C::M2T; t += q_warps) {
             mbar_wait(bar_mma2 + t, par);
@@ -738,28 +620,6 @@ template <class C>
 static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) return fail(HSB_ERR_CUDA, "patch_ir_tc: cuTensorMapEncodeTiled is not available from the driver");
-#ifdef HSB_IR_X5D
-    // 5-D view (innermost first): 8 pixels | channel | 8-pixel chunk of the row | row | image
-    CUtensorMap map, hmap;
-    const cuuint64_t dims[5] = {8, (cuuint64_t)C::CIN, (cuuint64_t)p.W / 8, (cuuint64_t)p.H, (cuuint64_t)p.B};
-    // HSB_IR_XBLOCKED=1: x is stored (B, H, W/8, C, 8) -- the layout a fused level-input kernel would write -- so that a
-    // (row, chunk) of the box is ONE contiguous run of C*16 bytes instead of C separate 16-byte rows
-    static const bool blocked = [] { const char* v = getenv("HSB_IR_XBLOCKED"); return v && v[0] == '1'; }();
-    const cuuint64_t s_nchw[4] = {(cuuint64_t)p.W * p.H * 2, 16, (cuuint64_t)p.W * 2, (cuuint64_t)p.W * p.H * C::CIN * 2};
-    const cuuint64_t s_blk[4] = {16, (cuuint64_t)C::CIN * 16, (cuuint64_t)(p.W / 8) * C::CIN * 16,
-                                 (cuuint64_t)p.H * (p.W / 8) * C::CIN * 16};
-    const cuuint64_t* strides = blocked ? s_blk : s_nchw;
-    const cuuint32_t box[5] = {8, (cuuint32_t)C::K1, (cuuint32_t)C::XCH, (cuuint32_t)C::TH, 1};
-    const cuuint32_t hbox[5] = {8, (cuuint32_t)C::K1, 1, (cuuint32_t)C::TH, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r == CUDA_SUCCESS)
-        r = encode(&hmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, hbox, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-#else
     CUtensorMap map;
     const cuuint64_t dims[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)C::CIN, (cuuint64_t)p.B};
     const cuuint64_t strides[3] = {(cuuint64_t)p.W * 2, (cuuint64_t)p.W * p.H * 2, (cuuint64_t)p.W * p.H * C::CIN * 2};
@@ -769,7 +629,6 @@ static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HSB_ERR_CUDA, "patch_ir_tc: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-#endif
     auto kern = patch_ir_tc_kernel<C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("patch_ir_tc attr: ") + cudaGetErrorString(e));
@@ -793,11 +652,7 @@ static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
         cudaMemsetAsync(dprof, 0, 4096 * 12 * sizeof(long long), st);
         IRTCParams pp = p;
         pp.prof = dprof;
-#ifdef HSB_IR_X5D
-        kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, hmap, pp);
-#else
         kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, pp);
-#endif
         cudaStreamSynchronize(st);
         static long long host[4096 * 12];
         cudaMemcpy(host, dprof, sizeof(long long) * grid * 12, cudaMemcpyDeviceToHost);
@@ -812,11 +667,8 @@ static int launch_tc(const void* x, const IRTCParams& p, cudaStream_t st) {
         return check_launch("patch_ir_tc launch");
     }
 #endif
-#ifdef HSB_IR_X5D
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, hmap, p);
-#else
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(map, p);
-#endif
+    note_kernel("patch_ir_tc_kernel");
     return check_launch("patch_ir_tc launch");
 }
 

@@ -130,5 +130,6 @@ extern "C" int hsb_signal2weights_fwd(const void* s, const void* ws, void* w_out
     dim3 grid((unsigned)ntiles, groups * p.otiles);
     if (dtype == HSB_F32) signal2weights_kernel<float><<<grid, 256, 0, st>>>(p);
     else signal2weights_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
+    note_kernel("signal2weights_kernel");
     return check_launch("signal2weights launch");
 }

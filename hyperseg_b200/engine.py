@@ -107,15 +107,6 @@ class SegmentationEngine:
             for m in self.net.modules():
                 if isinstance(m, FoldedBatchNorm):
                     m.shift32 = m.shift_master.to(self.device, torch.float32).contiguous()
-            if os.environ.get("HSB_FUSED_DW", "0") == "1" and dtype == torch.bfloat16:
-                # experimental, off by default until it has been validated on a GPU: depthwise conv fused with its epilogue
-                from .nn.efficientnet import MBConvBlock
-                for m in self.net.modules():
-                    if isinstance(m, MBConvBlock) and m.has_se and isinstance(m._bn1, FoldedBatchNorm):
-                        w = m._depthwise_conv.weight
-                        k = w.shape[-1]
-                        if w.shape[-2] == k and k in (3, 5) and m._depthwise_conv.stride[0] in (1, 2) and w.shape[0] % 8 == 0:
-                            m._dw_taps = w.detach().float().reshape(w.shape[0], k * k).t().contiguous()
         self.stream = torch.cuda.Stream(self.device)
         self.frames_dev = torch.zeros(self.shape, device=self.device, dtype=torch.float32)
         self.host_out = torch.empty((batch, height, width), dtype=torch.uint8).pin_memory()

@@ -116,16 +116,7 @@ class MBConvBlock(nn.Module):
         if self.expand:
             y = _norm_act(self._bn0, self._expand_conv(y), True)
         if self.has_se:
-            if getattr(self, "_dw_taps", None) is not None and ops.nhwc_epilogue_ok(y) and y.dtype == torch.bfloat16:
-                # experimental engine path (HSB_FUSED_DW=1): depthwise conv + shift + swish + SE sums in one kernel
-                dw = self._depthwise_conv
-                k, st = dw.kernel_size[0], dw.stride[0]
-                pt, pl = (dw.conv_pad if dw.symmetric else (dw.same_pad[2], dw.same_pad[0]))
-                pb, pr = (dw.conv_pad if dw.symmetric else (dw.same_pad[3], dw.same_pad[1]))
-                out_hw = ((y.shape[2] + pt + pb - k) // st + 1, (y.shape[3] + pl + pr - k) // st + 1)
-                y, squeezed = ops.dwconv_bias_act_nhwc(y, self._dw_taps, self._bn1.shift32, k, st, pt, pl, out_hw, "silu", pool=True)
-            else:
-                y, squeezed = _norm_act(self._bn1, self._depthwise_conv(y), True, pool=True)
+            y, squeezed = _norm_act(self._bn1, self._depthwise_conv(y), True, pool=True)
             fused = squeezed.dim() == 3         # engine path: per-chunk sums from the epilogue kernel (N, chunks, C)
             if fused:
                 squeezed = ops.pooled_mean(squeezed, y.shape[2] * y.shape[3], y.dtype)

@@ -524,27 +524,6 @@ def pooled_mean(partial, hw, dtype):
     return partial.sum(dim=1).mul_(1.0 / hw).to(dtype).view(N, C, 1, 1)
 
 
-def dwconv_bias_act_nhwc(x, w_taps, bias, k, stride, pad_top, pad_left, out_hw, act="none", pool=False):
-    """EXPERIMENTAL (HSB_FUSED_DW=1): depthwise k x k convolution + bias + activation (+ SE partial sums) in one pass over
-    a channels-last bf16 tensor.  ``w_taps`` is the (k*k, C) float32 transpose of the depthwise weight."""
-    if not nhwc_epilogue_ok(x) or x.dtype != torch.bfloat16:
-        raise ValueError("dwconv_bias_act_nhwc needs a channels-last bf16 CUDA tensor with 16-byte channel rows")
-    N, C, H, W = x.shape
-    Ho, Wo = out_hw
-    if tuple(w_taps.shape) != (k * k, C) or w_taps.dtype != torch.float32 or not w_taps.is_contiguous():
-        raise ValueError("w_taps must be a contiguous float32 (k*k, C) tensor")
-    y = torch.empty((N, C, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
-    partial = None
-    if pool:
-        chunks = _lib.load().hsb_dwconv_nhwc_chunks(C, Ho, Wo, stride)
-        if chunks <= 0:
-            raise ValueError("bad geometry for the fused depthwise convolution")
-        partial = torch.empty((N, chunks, C), dtype=torch.float32, device=x.device)
-    _call("hsb_dwconv_bias_act_nhwc_fwd", x.data_ptr(), w_taps.data_ptr(), _fptr(bias), y.data_ptr(), _fptr(partial),
-          N, H, W, C, k, stride, pad_top, pad_left, Ho, Wo, ACTS[act], _DTYPES[x.dtype], _stream())
-    return (y, partial) if pool else y
-
-
 def channel_gate_nhwc_(x, gate):
     """In place: x <- x * sigmoid(gate[n, c]); ``gate`` is (N, C, 1, 1) (the excitation of squeeze-and-excitation)."""
     if not nhwc_epilogue_ok(x):

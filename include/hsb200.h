@@ -284,19 +284,6 @@ int hsb_bias_act_nhwc_fwd(const void* x, const float* bias, const void* residual
 int hsb_channel_gate_nhwc_fwd(const void* x, const void* gate, void* y, int N, int64_t HW, int C, int dtype,
                               void* stream);
 
-/*
- * EXPERIMENTAL (engine flag HSB_FUSED_DW=1; written in round 1, not yet run on a GPU): the encoder's depthwise
- * convolution fused with the epilogue above, y = act(dwconv_kxk(x) + bias[c]) on channels-last bf16 tensors
- * (MBConvBlock: _depthwise_conv + _bn1 + swish [+ SE mean], hyperseg/models/backbones/efficientnet.py:100-106).
- *   x (N, H, W, C), y (N, Ho, Wo, C); w_taps (k*k, C) float32 = conv weight (C,1,k,k) transposed, BN scale folded;
- *   k in {3, 5}, stride in {1, 2}; zero padding pad_top / pad_left (static "SAME": the rest of the window falls off
- *   the far edges); pool_partial (N, hsb_dwconv_nhwc_chunks(...), C) float32 or NULL.
- */
-int hsb_dwconv_nhwc_chunks(int C, int Ho, int Wo, int stride);
-int hsb_dwconv_bias_act_nhwc_fwd(const void* x, const float* w_taps, const float* bias, void* y, float* pool_partial,
-                                 int N, int H, int W, int C, int k, int stride, int pad_top, int pad_left,
-                                 int Ho, int Wo, int act, int dtype, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

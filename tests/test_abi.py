@@ -32,6 +32,27 @@ def test_header_and_binding_agree(lib):
     assert len(syms) >= 9
 
 
+def _prototypes():
+    """name -> list of parameter kinds ('ptr' / 'i64' / 'int') parsed from the header."""
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int64_t|int|const\s+char\s*\*)\s+(hsb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        params = [p.strip() for p in m.group(2).split(",") if p.strip() and p.strip() != "void"]
+        out[m.group(1)] = ["ptr" if "*" in p else ("i64" if "int64_t" in p else "int") for p in params]
+    return out
+
+
+def test_ctypes_signatures_match_the_header_prototypes(lib):
+    """Arity and pointer / int64 / int kind of every parameter: a drifted signature would otherwise only fail (or
+    silently corrupt arguments) at call time on a GPU."""
+    protos = _prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_int: "int", ctypes.c_int64: "i64"}
+    for name, argtypes in _lib.SIGNATURES.items():
+        got = [kinds.get(a, "ptr") for a in argtypes]          # POINTER(c_int) etc. count as pointers
+        assert got == protos[name], f"{name}: ctypes {got} vs header {protos[name]}"
+
+
 def test_every_declared_symbol_is_exported(lib):
     raw = ctypes.CDLL(str(_lib.LIB_PATH))
     for s in declared_symbols():
