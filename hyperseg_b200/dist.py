@@ -41,19 +41,23 @@ def shard_batch(batch: torch.Tensor, rank: int | None = None, world_size: int | 
 
 
 def gather_logits(local: torch.Tensor, total_items: int | None = None) -> torch.Tensor:
-    """Concatenate the per-rank outputs along dim 0 on every rank (shards may differ by one item)."""
+    """Concatenate the per-rank outputs along dim 0 on every rank.  Shards may be ragged (B % world != 0): the ranks
+    first exchange their shard sizes (one tiny all_gather), then gather shards padded to the largest one and trim.
+    ``total_items`` is only checked against the exchanged sizes."""
     rank, w = world()
     if w == 1:
         return local
-    counts = None
-    if total_items is not None:
-        counts = [shard_bounds(total_items, r, w)[1] - shard_bounds(total_items, r, w)[0] for r in range(w)]
-    if counts is None or len(set(counts)) == 1:
+    mine = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
+    sizes = [torch.empty_like(mine) for _ in range(w)]
+    dist.all_gather(sizes, mine)
+    counts = [int(c.item()) for c in sizes]
+    if total_items is not None and sum(counts) != total_items:
+        raise ValueError(f"shards hold {sum(counts)} items, expected {total_items}")
+    m = max(counts)
+    if all(c == m for c in counts):
         out = [torch.empty_like(local) for _ in range(w)]
         dist.all_gather(out, local.contiguous())
         return torch.cat(out, 0)
-    # ragged: pad every shard to the largest one, gather, then trim
-    m = max(counts)
     pad = local.new_zeros((m,) + tuple(local.shape[1:]))
     pad[:local.shape[0]] = local
     out = [torch.empty_like(pad) for _ in range(w)]
@@ -65,7 +69,7 @@ def confusion_matrix(pred: torch.Tensor, target: torch.Tensor, num_classes: int,
     """num_classes x num_classes int64 counts, rows = ground truth, columns = prediction (seg_utils.py:10-17)."""
     pred = pred.reshape(-1).long()
     target = target.reshape(-1).long()
-    keep = (target != ignore_index) & (target >= 0) & (target < num_classes)
+    keep = (target != ignore_index) & (target >= 0) & (target < num_classes) & (pred >= 0) & (pred < num_classes)
     idx = target[keep] * num_classes + pred[keep]
     return torch.bincount(idx, minlength=num_classes * num_classes).reshape(num_classes, num_classes)
 

@@ -127,19 +127,25 @@ class HyperPatchInvertedResidual(nn.Module, _SignalHeadMixin):
         self._check_supported()
         sig_index = int(self.signal_index if signal_index is None else signal_index)
         sig_ch = int(self.signal_channels if signal_channels is None else signal_channels)
-        bns = [ops.fold_bn(bn) for bn in (self.bn1, self.bn2, self.bn3)]
+        norms = (self.bn1, self.bn2, self.bn3)
         key = (head.weight.data_ptr(), head.weight._version, head.weight.dtype, sig_index, sig_ch, int(hp_offset),
-               tuple(t.data_ptr() for pair in bns for t in pair),
-               tuple(t._version for bn in (self.bn1, self.bn2, self.bn3) for t in (bn.running_mean, bn.running_var) if t is not None))
+               tuple((t.data_ptr(), t._version) for bn in norms for t in (bn.running_mean, bn.running_var, bn.weight, bn.bias)
+                     if t is not None),
+               tuple(id(getattr(bn, "_hsb_folded", None)) for bn in norms))
         cached = getattr(self, "_hsb_arranged", None)
         if cached is None or cached[0] != key:
+            bns = [ops.fold_bn(bn) for bn in norms]
+            bns = [(a.to(x.device, torch.float32).contiguous(), b.to(x.device, torch.float32).contiguous()) for a, b in bns]
             try:
                 packed = ops.ArrangedHead(head.weight, sig_index, sig_ch, head.groups, int(hp_offset), self.in_nc, self.hidden_dim,
                                           self.out_nc, bns[0][0], bns[1][0], bns[2][0])
             except ops._lib.HsbError:
                 packed = None                              # a tile of this head needs too wide a signal range
-            cached = (key, packed, bns)                    # keeps the folded BatchNorm tensors (and so their addresses) alive
+            # the packed operand, its tile table and the folded shifts live as long as this module: a CUDA graph captured
+            # over this call keeps reading them
+            cached = (key, packed, bns)
             self._hsb_arranged = cached
+        bns = cached[2]
         if cached[1] is None:
             return None
         w_arr = ops.signal2weights_arranged(s, cached[1])

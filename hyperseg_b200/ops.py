@@ -320,8 +320,11 @@ def _cache_lookup(cache, key, owner):
 
 
 def _cache_store(cache, key, owner, value, limit=64):
+    """Entries whose owner is alive are never evicted: a captured CUDA graph may have the packed buffer's address baked
+    in.  Only entries of dead owners (which can never hit again) are pruned once the table grows."""
     if len(cache) > limit:
-        cache.clear()
+        for k in [k for k, (ref, _) in cache.items() if ref() is None]:
+            del cache[k]
     cache[key] = (weakref.ref(owner), value)
 
 

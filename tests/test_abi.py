@@ -127,6 +127,7 @@ def test_packed_head_cache_is_tied_to_the_live_tensor_object():
     del b
     gc.collect()
     assert cache[key][0]() is None                               # dead owner: the entry can never hit again
-    for i in range(70):                                          # bounded
+    for i in range(70):                                          # live owners are never evicted (a CUDA graph may read them)
         ops._cache_store(cache, ("k", i), a, i)
-    assert len(cache) <= 66
+    assert all(ops._cache_lookup(cache, ("k", i), a) == i for i in range(70))
+    assert key not in cache                                      # ... dead ones are pruned once the table grows
