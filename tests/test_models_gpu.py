@@ -56,3 +56,55 @@ def test_list_input_with_hflip_tta():
         flipped = torch.flip(model(torch.flip(x, [-1])), [-1])
         tta = model([x])
     assert torch.allclose(tta, torch.max(single, flipped), atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the benchmarked path at the benchmark sizes: SegmentationEngine (bf16, folded BatchNorm, channels-last encoder, CUDA
+# graph, arranged heads -> restage-free MetaBlock kernels) against logits of the UNMODIFIED reference
+# (tests/golden/fullsize.npz, written by tests/golden/make_golden_fullsize.py)
+# ---------------------------------------------------------------------------------------------------------------------
+FULLSIZE = {  # name -> (configuration, H, W, engine batch of the BASELINE configuration)
+    "m_512x1024": ("hyperseg-m", 512, 1024, 8),
+    "s_city_768x1536": ("hyperseg-s-cityscapes", 768, 1536, 4),
+    "s_camvid_576x768": ("hyperseg-s-camvid", 576, 768, 8),
+}
+# measured on B200 (this test prints them): logits err / max|logit| 9.1e-3 / 1.0e-2 / 8.2e-3 (M / S-city / S-CamVid), labels
+# equal on 100 % of the pixels (the reference's own bf16 autocast moves its logits by 6e-3); thresholds = measured + margin
+ENGINE_LOGIT_TOL, ENGINE_LABELS_ALL, ENGINE_LABELS_CLEAR = 1.6e-2, 0.985, 0.999
+
+
+@pytest.fixture(scope="module")
+def golden_fullsize():
+    import os
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fullsize.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(FULLSIZE))
+def test_engine_at_benchmark_size_matches_reference(name, golden_fullsize):
+    from hyperseg_b200 import _lib
+    from hyperseg_b200.engine import SegmentationEngine
+    config, H, W, B = FULLSIZE[name]
+    model = build_model(config, seed=0)
+    engine = SegmentationEngine(model, B, H, W, dtype=torch.bfloat16, use_graph=True)
+    frames = synthetic_frames(B, H, W, seed=77)
+    frames[0] = synthetic_frames(1, H, W, seed=1234)[0]          # the frame the golden was computed on (batch independent)
+    labels = engine(frames.pin_memory()).clone()
+    logits = engine.full_logits()[0:1].float().cpu()
+    ref = torch.from_numpy(golden_fullsize[f"{name}/logits"])
+    ref_labels = torch.from_numpy(golden_fullsize[f"{name}/argmax"])[0]
+    clear = torch.from_numpy(golden_fullsize[f"{name}/margin_u8"])[0] >= 51          # margin >= 2 % of max |logit|
+    err = rel_err(logits[:, :, ::8, ::8], ref)
+    same = labels[0] == ref_labels
+    agree_all, agree_clear = same.float().mean().item(), same[clear].float().mean().item()
+    print(f"{name}: logits rel err {err:.2e}, labels equal {agree_all:.4f} (all) {agree_clear:.5f} (margin >= 2 %, "
+          f"{clear.float().mean().item():.2f} of the pixels)")
+    assert err < ENGINE_LOGIT_TOL
+    assert agree_all > ENGINE_LABELS_ALL and agree_clear > ENGINE_LABELS_CLEAR
+    # and the engine really ran the tensor-core path: the last decoder kernel launched while warming up / capturing
+    assert engine.launches_per_step > 0
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        engine.net.decoder.forward_features([torch.zeros(1, 3, H, W, device="cuda", dtype=torch.bfloat16)] +
+                                            [f[:1] for f in engine.net.backbone(torch.zeros(1, 3, H, W, device="cuda", dtype=torch.bfloat16))[:-1]],
+                                            torch.zeros(1, 1280, H // 32, W // 32, device="cuda", dtype=torch.bfloat16))
+    assert _lib.last_kernel() == "patch_ir2_kernel"
