@@ -106,7 +106,7 @@ struct IR2 {
     static constexpr int OFF_A1 = 0, OFF_A2 = OFF_A1 + 2 * SZ_A1, OFF_HID = OFF_A2 + 2 * SZ_A2;
     static constexpr int OFF_W1 = OFF_HID + 2 * SZ_HID, OFF_W23 = OFF_W1 + 2 * SZ_W1;
     static constexpr int OFF_SAVE = OFF_W23 + 2 * SZ_W23;
-    static constexpr int OFF_B2B = OFF_SAVE + 2 * SZ_SAVE, OFF_BAR = OFF_B2B + ir_r16(HID * 2);
+    static constexpr int OFF_B2B = OFF_SAVE + 3 * SZ_SAVE, OFF_BAR = OFF_B2B + ir_r16(HID * 2);
     static constexpr int NBAR = 40;
     static constexpr int USED_BYTES = OFF_BAR + NBAR * 8 + 16, SMEM_BYTES = USED_BYTES + 1024;
     static constexpr int CTAS = 1;
@@ -137,11 +137,15 @@ struct IR2Maps { CUtensorMap lo, lo_tail, hi, hi_tail, y; };   // x boxes of LO_
 // profiling build: cycles a role's lane spends in each of its waits, and in its whole loop
 #ifdef HSB_IR_PROF
 #define PWAIT(slot, bar, par) do { long long t0_ = clock64(); mbar_wait_suspend(bar, par); prof_acc[slot] += clock64() - t0_; } while (0)
-#define PROF_BEGIN() long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64()
+#define PROF_BEGIN() long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64(); long long prof_seg = prof_t0
+#define PSEG_RESET() do { prof_seg = clock64(); } while (0)
+#define PSEG(slot) do { long long n_ = clock64(); prof_acc[slot] += n_ - prof_seg; prof_seg = n_; } while (0)
 #define PROF_END(role, cond) do { if (cond) { prof_acc[7] = clock64() - prof_t0; for (int k_ = 0; k_ < 8; ++k_) p.prof[((size_t)blockIdx.x * 8 + role) * 8 + k_] = prof_acc[k_]; } } while (0)
 #else
 #define PWAIT(slot, bar, par) mbar_wait_suspend(bar, par)
 #define PROF_BEGIN() do { } while (0)
+#define PSEG_RESET() do { } while (0)
+#define PSEG(slot) do { } while (0)
 #define PROF_END(role, cond) do { } while (0)
 #endif
 
@@ -186,7 +190,9 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
     unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // mbarriers.  "full" = data ready for the consumer, "empty" = buffer may be overwritten by the producer.
+    // mbarriers.  "full" = data ready for the consumer, "empty" = buffer may be overwritten by the producer.  Roles made of
+    // whole warps arrive once per warp (lane 0, after __syncwarp has ordered the warp's shared-memory traffic before it):
+    // a 32-lane arrive on one barrier would be 32 serialised shared-memory atomics.
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
     uint64_t* lo_full = bars;            // [2] body rows [0, LO_ROWS) of the x tile landed (TMA transaction bytes)
     uint64_t* hi_full = bars + 2;        // [2] remaining body rows + B1 landed
@@ -231,18 +237,18 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
             mbar_init(hi_full + s, 1);
             mbar_init(lo_empty + s, 1);
             mbar_init(hi_empty + s, 1);
-            mbar_init(body_ready + s, 32 * C::PRODN);
-            mbar_init(halo_ready + s, 32 * C::PRODN);
+            mbar_init(body_ready + s, C::PRODN);
+            mbar_init(halo_ready + s, C::PRODN);
             mbar_init(w23_full + s, 1);
             for (int t = 0; t < 3; ++t) mbar_init(acc1_full + s * 3 + t, 1);
-            mbar_init(acc1_empty + s, 128);
-            mbar_init(hid_full + s, 128);
-            mbar_init(hid_empty + s, 32 * C::DWN);
-            mbar_init(a2_full + s, 32 * C::WPH);
+            mbar_init(acc1_empty + s, 4);
+            mbar_init(hid_full + s, 4);
+            mbar_init(hid_empty + s, C::DWN);
+            mbar_init(a2_full + s, C::WPH);
             mbar_init(a2_empty + s, 1);
         }
         mbar_init(acc2_full, 1);
-        mbar_init(acc2_empty, 128);
+        mbar_init(acc2_empty, 4);
         mbar_fence_init();
         tma_prefetch_desc(&maps.lo);
         tma_prefetch_desc(&maps.lo_tail);
@@ -267,28 +273,39 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
         // Halo column sources (same tile rows everywhere): the left column of patch n is body column PS-1 of patch n-1,
         // saved when that tile landed; its right column is body column 0 of patch n+1, written one iteration later, when
         // that tile has landed; at the image border the mirror column of the own body; at the two ends of the CTA's run
-        // global memory.  All reads of the tile happen before body_ready is signalled: the body tiles of GEMM1 may then
-        // run and release rows [0, LO_ROWS) of the stage to the loader.
+        // global memory.  An iteration has two passes: pass A over tile rows [0, LO_ROWS) as soon as that part of the
+        // tile has landed -- it ends with body_ready, after which the body tiles of GEMM1 may run and release those rows
+        // to the loader -- and a short pass B over the remaining rows, which is all that stands between the arrival of
+        // the tile's last rows and the last GEMM1 tile of the PREVIOUS patch (its right halo column).
         const int ptid = tid - 32 * C::W_PROD;
-        constexpr int PT = 32 * C::PRODN, NE = C::CIN * C::TH;   // NE (channel, tile row) pairs per halo column
+        constexpr int PT = 32 * C::PRODN, NE = C::CIN * C::TH, NE_LO = C::CIN * C::LO_ROWS, NE_HI = NE - NE_LO;
         const size_t HW = (size_t)p.H * p.W;
         auto swz = [](uint32_t o) { return C::PS == 16 ? (o ^ (((o >> 7) & 1u) << 4)) : o; };
+        // pair index -> (channel, tile row): channel fastest, so that neighbouring lanes hit different banks
         auto body_off = [](int e) { const int c = e % C::CIN, r = e / C::CIN; return (uint32_t)((c >> 3) * C::A1_KGS + r * C::GRP + (c & 7) * C::ROWB); };
         auto slot_off = [&](int e, int side) {
             const int c = e % C::CIN, r = e / C::CIN, h = side * C::TH + r;
             return swz((uint32_t)((c >> 3) * C::A1_KGS + (C::TH + h / C::PS) * C::GRP + (c & 7) * C::ROWB + (h % C::PS) * 2));
         };
+        auto lds16 = [](uint32_t addr) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory"); return v; };
+        auto sts16 = [](uint32_t addr, unsigned short v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory"); };
         // (1) what the neighbours need from a tile that has just landed: even lanes read its last column (saved: left halo of
-        //     the next patch), odd lanes its first column (right halo of the previous patch).  Channel fastest over lane
-        //     pairs, the two columns in different banks: two-way bank conflicts instead of eight-way.
-        constexpr int NT1 = (NE + PT / 2 - 1) / (PT / 2);
-        const int role = ptid & 1;
-        uint32_t t1[NT1];        // body offset | right halo slot offset << 16; 0xFFFFFFFF = no task
+        //     the next patch), odd lanes its first column (right halo of the previous patch) -- the two columns sit in
+        //     different banks, so a warp sees two-way instead of four-way conflicts.  Tasks are split by the part of the
+        //     tile they read (rows [0, LO_ROWS) / the rest) and fully described by two 16-bit offsets each: source inside
+        //     the stage, destination inside the save buffer (even lanes) or inside the other stage (odd lanes).
+        const int role = ptid & 1, pair = ptid >> 1;
+        constexpr int NT_LO = (NE_LO + PT / 2 - 1) / (PT / 2), NT_HI = (NE_HI + PT / 2 - 1) / (PT / 2);
+        uint32_t t_lo[NT_LO], t_hi[NT_HI > 0 ? NT_HI : 1];     // src | dst << 16; dst 0xFFFF = no task (reads offset 0, stores nothing)
+        auto make_task = [&](int e) {
+            const uint32_t src = swz(body_off(e) + 2 * (role == 0 ? C::PS - 1 : 0));
+            const uint32_t dst = role == 0 ? (uint32_t)(2 * e) : slot_off(e, 1);
+            return src | (dst << 16);
+        };
 #pragma unroll
-        for (int j = 0; j < NT1; ++j) {
-            const int e = (ptid >> 1) + j * (PT / 2);
-            t1[j] = e < NE ? (body_off(e) | (slot_off(e, 1) << 16)) : 0xFFFFFFFFu;
-        }
+        for (int j = 0; j < NT_LO; ++j) { const int e = pair + j * (PT / 2); t_lo[j] = e < NE_LO ? make_task(e) : 0xFFFF0000u; }
+#pragma unroll
+        for (int j = 0; j < NT_HI; ++j) { const int e = NE_LO + pair + j * (PT / 2); t_hi[j] = e < NE ? make_task(e) : 0xFFFF0000u; }
         // (2) halo columns written from somewhere else (saved column, own mirror column, global memory): all lanes
         constexpr int NT2 = (NE + PT - 1) / PT;
         uint32_t t2[NT2];        // left slot offset | right slot offset << 16
@@ -299,15 +316,14 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
             t2[j] = e < NE ? (slot_off(e, 0) | (slot_off(e, 1) << 16)) : 0xFFFFFFFFu;
             t2b[j] = e < NE ? body_off(e) : 0;
         }
-        auto own_col = [&](unsigned char* stage, int col, int side) {
+        auto own_col = [&](uint32_t stage, int col, int side, int pass) {
 #pragma unroll
             for (int j = 0; j < NT2; ++j)
-                if (t2[j] != 0xFFFFFFFFu)
-                    *reinterpret_cast<unsigned short*>(stage + ((t2[j] >> (16 * side)) & 0xFFFFu)) =
-                        *reinterpret_cast<const unsigned short*>(stage + swz(t2b[j] + 2 * col));
+                if (t2[j] != 0xFFFFFFFFu && ((ptid + j * PT < NE_LO) == (pass == 0)))
+                    sts16(stage + ((t2[j] >> (16 * side)) & 0xFFFFu), lds16(stage + swz(t2b[j] + 2 * col)));
         };
         // column gx of the image (rows reflected at the top / bottom border) -> halo slots: only at the ends of the run
-        auto copy_global = [&](const PatchWalk& w, int gx, unsigned char* stage, int side) {
+        auto copy_global = [&](const PatchWalk& w, int gx, uint32_t stage, int side) {
             const unsigned short* xb = reinterpret_cast<const unsigned short*>(p.x) + (size_t)w.b * C::CIN * HW;
 #pragma unroll
             for (int j = 0; j < NT2; ++j) {
@@ -316,7 +332,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                     const int c = e % C::CIN, r = e / C::CIN;
                     int gy = w.pi * C::PS - 1 + r;
                     gy = gy < 0 ? -gy : (gy >= p.H ? 2 * p.H - 2 - gy : gy);
-                    *reinterpret_cast<unsigned short*>(stage + ((t2[j] >> (16 * side)) & 0xFFFFu)) = __ldg(xb + (size_t)c * HW + (size_t)gy * p.W + gx);
+                    sts16(stage + ((t2[j] >> (16 * side)) & 0xFFFFu), __ldg(xb + (size_t)c * HW + (size_t)gy * p.W + gx));
                 }
             }
         };
@@ -325,58 +341,74 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
         for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
             const uint32_t s = it & 1, ph = (it >> 1) & 1;
             unsigned char* a1 = sm + C::OFF_A1 + s * C::SZ_A1;
-            unsigned char* a1_prev = sm + C::OFF_A1 + (s ^ 1) * C::SZ_A1;
-            unsigned short* save = reinterpret_cast<unsigned short*>(sm + C::OFF_SAVE + s * C::SZ_SAVE);
-            const unsigned short* save_prev = reinterpret_cast<const unsigned short*>(sm + C::OFF_SAVE + (s ^ 1) * C::SZ_SAVE);
+            const uint32_t a1s = sm_base + C::OFF_A1 + s * C::SZ_A1, a1s_prev = sm_base + C::OFF_A1 + (s ^ 1) * C::SZ_A1;
+            // three buffers: the column saved in iteration i is read in iteration i+1, while faster warps may already be
+            // saving in iteration i+2 (the named barrier below keeps the warps within one iteration of each other)
+            const uint32_t save = sm_base + C::OFF_SAVE + (it % 3) * C::SZ_SAVE, save_prev = sm_base + C::OFF_SAVE + ((it + 2) % 3) * C::SZ_SAVE;
             const int x0 = pw.pj * C::PS;
             const bool top = pw.pi == 0, bottom = pw.pi == p.fh - 1;
             const bool first_col = pw.pj == 0, last_col = pw.pj == p.fw - 1;
             const bool right_next = !last_col && pw.patch + 1 < n1;
-            // the left halo column that was saved from the previous tile does not need this tile: fetch it first
             const bool left_saved = !first_col && it > 0;
-            unsigned short lv[NT2];
+            // the halo groups of this stage are free once the last GEMM1 tile of the patch two steps back has retired
+            mbar_wait_suspend(hi_empty + s, ph ^ 1);
+            named_bar_sync(3, PT);                         // columns saved by other lanes in the previous iteration are visible
             if (left_saved) {
-                named_bar_sync(3, PT);                     // the column was saved by other lanes in the previous iteration
+                unsigned short lv[NT2];
 #pragma unroll
-                for (int j = 0; j < NT2; ++j) lv[j] = t2[j] != 0xFFFFFFFFu ? save_prev[ptid + j * PT] : (unsigned short)0;
-            }
-            PWAIT(0, lo_full + s, ph);                      // the tile has landed
-            PWAIT(1, hi_full + s, ph);
-            if (top || bottom) {                           // tile row 0 <- row 2, row TH-1 <- row TH-3 (whole M-groups)
-                for (int i = ptid; i < C::KC1 * (C::GRP / 16); i += PT) {
-                    unsigned char* base = a1 + (i / (C::GRP / 16)) * C::A1_KGS + (i % (C::GRP / 16)) * 16;
-                    if (top) *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(base + 2 * C::GRP);
-                    if (bottom) *reinterpret_cast<uint4*>(base + (C::TH - 1) * C::GRP) = *reinterpret_cast<const uint4*>(base + (C::TH - 3) * C::GRP);
+                for (int j = 0; j < NT2; ++j) lv[j] = lds16(save_prev + 2 * min(ptid + j * PT, NE - 1));
+#pragma unroll
+                for (int j = 0; j < NT2; ++j)
+                    if (t2[j] != 0xFFFFFFFFu) sts16(a1s + (t2[j] & 0xFFFFu), lv[j]);
+            } else if (!first_col) copy_global(pw, x0 - 1, a1s, 0);
+            if (!last_col && !right_next) copy_global(pw, x0 + C::PS, a1s, 1);
+            // the columns the neighbours need: destination base of this lane's tasks (save buffer / the other stage)
+            const bool copy_on = role == 0 ? right_next : prev_deferred;
+            const uint32_t dst_base = role == 0 ? save : a1s_prev;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 0) PWAIT(0, lo_full + s, ph); else PWAIT(1, hi_full + s, ph);      // that part of the tile has landed
+                // mirror rows (whole M-groups): tile row 0 <- row 2 (pass A), row TH-1 <- row TH-3 (the pass that owns row TH-1)
+                const bool do_top = top && pass == 0, do_bottom = bottom && pass == (C::HI_ROWS > 0 ? 1 : 0);
+                if (do_top || do_bottom) {
+                    for (int i = ptid; i < C::KC1 * (C::GRP / 16); i += PT) {
+                        unsigned char* base = a1 + (i / (C::GRP / 16)) * C::A1_KGS + (i % (C::GRP / 16)) * 16;
+                        if (do_top) *reinterpret_cast<uint4*>(base) = *reinterpret_cast<const uint4*>(base + 2 * C::GRP);
+                        if (do_bottom) *reinterpret_cast<uint4*>(base + (C::TH - 1) * C::GRP) = *reinterpret_cast<const uint4*>(base + (C::TH - 3) * C::GRP);
+                    }
+                    named_bar_sync(2, PT);                 // the column copies below read the mirrored rows
                 }
-                named_bar_sync(2, PT);                     // the column copies below read the mirrored rows
-            }
-            if (role == 0 ? right_next : prev_deferred) {
-                unsigned short v[NT1];
-                const int col = role == 0 ? C::PS - 1 : 0;
+                if (copy_on) {
+                    if (pass == 0) {
+                        unsigned short v[NT_LO];
 #pragma unroll
-                for (int j = 0; j < NT1; ++j)
-                    v[j] = t1[j] != 0xFFFFFFFFu ? *reinterpret_cast<const unsigned short*>(a1 + swz((t1[j] & 0xFFFFu) + 2 * col)) : (unsigned short)0;
+                        for (int j = 0; j < NT_LO; ++j) v[j] = lds16(a1s + (t_lo[j] & 0xFFFFu));       // a missing task reads a valid (unused) address
 #pragma unroll
-                for (int j = 0; j < NT1; ++j) {
-                    if (t1[j] != 0xFFFFFFFFu) {
-                        if (role == 0) save[(ptid >> 1) + j * (PT / 2)] = v[j];
-                        else *reinterpret_cast<unsigned short*>(a1_prev + (t1[j] >> 16)) = v[j];
+                        for (int j = 0; j < NT_LO; ++j)
+                            if (j < NT_LO - 1 || (t_lo[j] >> 16) != 0xFFFFu) sts16(dst_base + (t_lo[j] >> 16), v[j]);
+                    } else if (C::HI_ROWS > 0) {
+                        unsigned short v[NT_HI > 0 ? NT_HI : 1];
+#pragma unroll
+                        for (int j = 0; j < NT_HI; ++j) v[j] = lds16(a1s + (t_hi[j] & 0xFFFFu));
+#pragma unroll
+                        for (int j = 0; j < NT_HI; ++j)
+                            if ((t_hi[j] >> 16) != 0xFFFFu) sts16(dst_base + (t_hi[j] >> 16), v[j]);
+                    }
+                }
+                if (C::HI_ROWS > 0 || pass == 0) {          // mirror columns of this patch at the image border
+                    if (first_col) own_col(a1s, 1, 0, pass);
+                    if (last_col) own_col(a1s, C::PS - 2, 1, pass);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (pass == 0) mbar_arrive(body_ready + s);
+                    else {
+                        if (prev_deferred) mbar_arrive(halo_ready + (s ^ 1));     // the previous patch may finish GEMM1
+                        if (!right_next) mbar_arrive(halo_ready + s);
                     }
                 }
             }
-            // halo columns of this patch that do not come from the next tile
-            if (left_saved) {
-#pragma unroll
-                for (int j = 0; j < NT2; ++j)
-                    if (t2[j] != 0xFFFFFFFFu) *reinterpret_cast<unsigned short*>(a1 + (t2[j] & 0xFFFFu)) = lv[j];
-            } else if (first_col) own_col(a1, 1, 0);
-            else copy_global(pw, x0 - 1, a1, 0);
-            if (last_col) own_col(a1, C::PS - 2, 1);
-            else if (!right_next) copy_global(pw, x0 + C::PS, a1, 1);
-            fence_proxy_async_smem();
-            mbar_arrive(body_ready + s);
-            if (prev_deferred) mbar_arrive(halo_ready + (s ^ 1));
-            if (!right_next) mbar_arrive(halo_ready + s);
             prev_deferred = right_next;
         }
         PROF_END(0, ptid == 0);
@@ -554,8 +586,11 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                 }
             }
             tc_fence_before_sync();
-            mbar_arrive(acc1_empty + s);
-            mbar_arrive(hid_full + s);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(acc1_empty + s);
+                mbar_arrive(hid_full + s);
+            }
         }
         PROF_END(3, tid == 0);
     } else if (warp < C::W_DW) {
@@ -602,7 +637,8 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                 }
                 tmem_ld_wait();
                 tc_fence_before_sync();
-                mbar_arrive(acc2_empty);                   // the next GEMM2 may overwrite the accumulator
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc2_empty);    // the next GEMM2 may overwrite the accumulator
                 if (pix < C::HALF_PX) {
 #pragma unroll
                     for (int c = 0; c < C::COUT; ++c)
@@ -723,30 +759,50 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
             }
             if (tail_lane) {                                // pixels of channels 64..67 (quad 16): weights are broadcast loads
                 if (!active && !ones_lane) PWAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1);
+                constexpr int TW = TAIL_PER % 2 == 0 ? 2 : 1;    // pixels per step: horizontally adjacent pairs share their window columns
+                const uint2 bq = *reinterpret_cast<const uint2*>(sm + C::OFF_B2B + 16 * 8);
+                __nv_bfloat162 wq[9][2];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const uint2 wv = *reinterpret_cast<const uint2*>(wbuf + t * C::HID * 2 + 16 * 8);
+                    wq[t][0] = *reinterpret_cast<const __nv_bfloat162*>(&wv.x);
+                    wq[t][1] = *reinterpret_cast<const __nv_bfloat162*>(&wv.y);
+                }
+                const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll 1
-                for (int k = 0; k < TAIL_PER; ++k) {
-                    const int tail_t = tih / TAIL_SKIP + k * (TPH / TAIL_SKIP);
+                for (int k = 0; k < TAIL_PER / TW; ++k) {
+                    const int tail_t = (tih / TAIL_SKIP + k * (TPH / TAIL_SKIP)) * TW;
                     const int tu = tail_t / C::PS, tv = tail_t % C::PS;
                     const unsigned char* src = hid + (size_t)((my_half * C::RPH + tu) * C::TH + tv) * C::HPITCH + 16 * 8;
-                    const uint2 bq = *reinterpret_cast<const uint2*>(sm + C::OFF_B2B + 16 * 8);
-                    __nv_bfloat162 acc[2] = {*reinterpret_cast<const __nv_bfloat162*>(&bq.x), *reinterpret_cast<const __nv_bfloat162*>(&bq.y)};
+                    __nv_bfloat162 hv[3][TW + 2][2];
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const uint2 wv = *reinterpret_cast<const uint2*>(wbuf + t * C::HID * 2 + 16 * 8);
-                        const uint2 hv = *reinterpret_cast<const uint2*>(src + ((t / 3) * C::TH + (t % 3)) * C::HPITCH);
-                        acc[0] = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&wv.x), *reinterpret_cast<const __nv_bfloat162*>(&hv.x), acc[0]);
-                        acc[1] = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&wv.y), *reinterpret_cast<const __nv_bfloat162*>(&hv.y), acc[1]);
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < TW + 2; ++c) {
+                            const uint2 v = *reinterpret_cast<const uint2*>(src + (r * C::TH + c) * C::HPITCH);
+                            hv[r][c][0] = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+                            hv[r][c][1] = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+                        }
+#pragma unroll
+                    for (int j = 0; j < TW; ++j) {
+                        __nv_bfloat162 acc[2] = {*reinterpret_cast<const __nv_bfloat162*>(&bq.x), *reinterpret_cast<const __nv_bfloat162*>(&bq.y)};
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            acc[0] = __hfma2(wq[t][0], hv[t / 3][j + t % 3][0], acc[0]);
+                            acc[1] = __hfma2(wq[t][1], hv[t / 3][j + t % 3][1], acc[1]);
+                        }
+                        acc[0] = __hmin2(__hmax2(acc[0], zero), six);
+                        acc[1] = __hmin2(__hmax2(acc[1], zero), six);
+                        *reinterpret_cast<uint2*>(dst + C::SZ_A2S + (tail_t + j) * 16) = make_uint2(*reinterpret_cast<uint32_t*>(&acc[0]), *reinterpret_cast<uint32_t*>(&acc[1]));
                     }
-                    const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
-                    acc[0] = __hmin2(__hmax2(acc[0], zero), six);
-                    acc[1] = __hmin2(__hmax2(acc[1], zero), six);
-                    *reinterpret_cast<uint2*>(dst + C::SZ_A2S + tail_t * 16) = make_uint2(*reinterpret_cast<uint32_t*>(&acc[0]), *reinterpret_cast<uint32_t*>(&acc[1]));
                 }
             }
-            __syncwarp();                                   // idle lanes must not run ahead and arrive twice in one phase
             fence_proxy_async_smem();
-            mbar_arrive(a2_full + hb);
-            mbar_arrive(hid_empty + s);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(a2_full + hb);
+                mbar_arrive(hid_empty + s);
+            }
         }
         PROF_END(5, dw == 0 && lane == 0);
         PROF_END(6, dw == C::DWN - 1 && lane == 0);
