@@ -125,7 +125,63 @@ def timing():
                 print(f"{name} {label}: {us:.1f} us/launch  {nbytes / us * 1e-3:.0f} GB/s  frac {nbytes / us * 1e-3 / 6539.5:.3f}  (min {min(ts) * 1e3:.1f} us, SM clock {clk[0]} MHz)", flush=True)
 
 
+def graph_time(fns, iters=12, reps=15):
+    with torch.no_grad():
+        for f in fns:
+            f()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            for f in fns:
+                f()
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(iters):
+                    fns[i % len(fns)]()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(side):
+                e0.record(side)
+                graph.replay()
+                e1.record(side)
+            side.synchronize()
+            ts.append(e0.elapsed_time(e1) / iters)
+    return sorted(ts)[len(ts) // 2] * 1e3
+
+
+def scan():
+    """Launch time against patches per CTA (batch 1..8 of the 16x32 grid): least-squares fixed cost + cost per patch."""
+    a = torch.randn(8192, 8192, device=DEV, dtype=torch.bfloat16)
+    for _ in range(30):
+        a @ a
+    torch.cuda.synchronize()
+    for name, (cin, hid, cout, h, w_) in {"ir": (34, 68, 19, 256, 512), "ir3": (24, 48, 16, 128, 256)}.items():
+        pts = []
+        for B in (1, 2, 3, 4, 6, 8):
+            fns = []
+            for k in range(3):
+                x = rnd((B, cin, h, w_), k).to(DEV, torch.bfloat16)
+                wt = ops.weights_to_patch_major(rnd((B, cin * hid + 9 * hid + hid * cout, 16, 32), 10 + k, 0.3).to(DEV, torch.bfloat16))
+                dev = [(a_.to(DEV), b_.to(DEV)) for a_, b_ in [bn(hid, 1), bn(hid, 2), bn(cout, 3)]]
+                wa = ops.ir_arrange_weights(wt, cin, hid, cout, dev[0][0], dev[1][0], dev[2][0])
+                fns.append(lambda x=x, wa=wa, dev=dev: ops.patch_ir_arranged(x, wa, hid, cout, dev[0][1], dev[1][1], dev[2][1]))
+            us = graph_time(fns)
+            per_cta = -(-B * 512 // 148)
+            pts.append((per_cta, us))
+            print(f"{name} B={B}: {per_cta} patches per CTA, {us:.1f} us", flush=True)
+        n = len(pts); sx = sum(p for p, _ in pts); sy = sum(u for _, u in pts)
+        sxx = sum(p * p for p, _ in pts); sxy = sum(p * u for p, u in pts)
+        b = (n * sxy - sx * sy) / (n * sxx - sx * sx); a0 = (sy - b * sx) / n
+        print(f"{name}: fixed {a0:.1f} us + {b:.2f} us per patch per CTA ({b * 1965:.0f} cycles at 1965 MHz)", flush=True)
+
+
 if __name__ == "__main__":
+    if "--scan" in sys.argv:
+        scan()
+        sys.exit(0)
     ok = True
     if "--time-only" not in sys.argv:
         ok = parity()

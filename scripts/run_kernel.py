@@ -38,6 +38,14 @@ elif which == "head4":
 elif which == "head0":
     s = rnd(B, 1280, 16, 32).abs(); ws = rnd(5248, 13, 1, 1, scale=0.2)
     fn = lambda: ops.signal2weights(s, ws, 0, 416, 5248, 32)
+elif which in ("head4a", "head3a"):
+    cin, hid, cout = (34, 68, 19) if which == "head4a" else (24, 48, 16)
+    hp = cin * hid + 9 * hid + hid * cout
+    sig, grp = (320, 4) if which == "head4a" else (192, 16)       # HyperSeg-M: level-4 / level-3 slices of the 1280-channel signal
+    s = rnd(B, 1280, 16, 32).abs(); ws = rnd(-(-hp // grp) * grp, sig // grp, 1, 1, scale=0.2)
+    s1, s2, s3 = bn(hid)[0], bn(hid)[0], bn(cout)[0]
+    hd = ops.ArrangedHead(ws, 0, sig, grp, 0, cin, hid, cout, s1, s2, s3)
+    fn = lambda: ops.signal2weights_arranged(s, hd)
 elif which == "epi":
     x = rnd(B, 96, 256, 512).contiguous(memory_format=torch.channels_last); sh = torch.randn(96, generator=g).to(dev)
     fn = lambda: ops.bias_act_nhwc_(x, sh, "silu", None, pool=True)

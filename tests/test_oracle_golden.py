@@ -106,3 +106,33 @@ def test_ir_per_patch_loop():
             out[0, :, i * ph:(i + 1) * ph, j * pw:(j + 1) * pw] = o
     out = out + x
     assert torch.allclose(y, out, atol=1e-12)
+
+
+def test_gpu_baseline_operator_sequence_matches_the_oracle():
+    """oracle/torch_gpu_baseline.py (the stock-ATen operator sequence bench.py times as ``gpu_reference``) computes the
+    same three functions as the float64 oracle: head, 1x1 block, inverted-residual block.  fp32 on CPU, tolerance 1e-5."""
+    from oracle import torch_gpu_baseline as tgb
+    g = torch.Generator().manual_seed(23)
+    B, fh, fw = 2, 2, 3
+    # head: groups 4, truncated to hp rows
+    s = torch.randn(B, 48, fh, fw, generator=g)
+    ws = torch.randn(72, 4, 1, 1, generator=g)
+    a = tgb.head(s, ws, 16, 16, 70, 4)
+    b = orc.signal2weights(s, ws, 16, 16, 70, 4)
+    assert rel_err(a, b) < 1e-5
+    # 1x1 block with BatchNorm + ReLU
+    x = torch.randn(B, 6, fh * 4, fw * 8, generator=g)
+    w = torch.randn(B, 6 * 5, fh, fw, generator=g)
+    scale, shift = torch.rand(5, generator=g) + 0.5, torch.randn(5, generator=g) * 0.1
+    a = tgb.patch_conv1x1(x, w, 5, tgb.make_bn(5, scale, shift, "cpu"), relu=True)
+    b = orc.patch_conv1x1(x, w, 5, scale=scale, shift=shift, act="relu")
+    assert rel_err(a, b) < 1e-5
+    # inverted-residual block
+    cin, hid, cout = 6, 12, 5
+    w = torch.randn(B, cin * hid + 9 * hid + hid * cout, fh, fw, generator=g) * 0.3
+    bns = [(torch.rand(n, generator=g) + 0.5, torch.randn(n, generator=g) * 0.1) for n in (hid, hid, cout)]
+    mods = [tgb.make_bn(n, sc, sh, "cpu") for n, (sc, sh) in zip((hid, hid, cout), bns)]
+    with torch.no_grad():
+        a = tgb.patch_ir(x, w, hid, cout, *mods)
+    b = orc.patch_ir(x, w, hid, cout, *bns)
+    assert rel_err(a, b) < 1e-5
