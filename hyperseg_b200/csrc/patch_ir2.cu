@@ -76,7 +76,7 @@ struct IR2 {
     static constexpr int SZ_A2S = 128 * 128, KT2 = K2 > 64 ? K2 - 64 : 0;
     static constexpr int A2T_LBO = 128 * 16, SZ_A2T = (KT2 / 8) * A2T_LBO;
     static constexpr int SZ_A2 = ir_r1024(SZ_A2S + SZ_A2T);
-    static constexpr int SZ_YST = COUT * HALF_PX * 2;           // output staging tile [c][u][v] of one half, inside A2
+    static constexpr int SZ_YST = ir_r128(COUT * HALF_PX * 2);  // output staging tile [c][u][v] of one half (source of the TMA store)
     // hidden tile [pixel][channel]
     static constexpr int HPITCH = ir_r8(HID) * 2, SZ_HID = ir_r128(T * HPITCH);
     // weight buffers: what the descriptors read past the data is zero, except the shift row
@@ -106,13 +106,15 @@ struct IR2 {
     static constexpr int OFF_A1 = 0, OFF_A2 = OFF_A1 + 2 * SZ_A1, OFF_HID = OFF_A2 + 2 * SZ_A2;
     static constexpr int OFF_W1 = OFF_HID + 2 * SZ_HID, OFF_W23 = OFF_W1 + 2 * SZ_W1;
     static constexpr int OFF_SAVE = OFF_W23 + 2 * SZ_W23;
-    static constexpr int OFF_B2B = OFF_SAVE + 3 * SZ_SAVE, OFF_BAR = OFF_B2B + ir_r16(HID * 2);
+    static constexpr int OFF_B2B = OFF_SAVE + 2 * SZ_SAVE, OFF_BAR = OFF_B2B + ir_r16(HID * 2);
     static constexpr int NBAR = 40;
-    static constexpr int USED_BYTES = OFF_BAR + NBAR * 8 + 16, SMEM_BYTES = USED_BYTES + 1024;
+    static constexpr int OFF_YST = ir_r128(OFF_BAR + NBAR * 8 + 16);
+    // the output staging tile is double-buffered where it fits (everywhere but the 34-68-19 block)
+    static constexpr int NYST = OFF_YST + 2 * SZ_YST <= 227 * 1024 ? 2 : 1;
+    static constexpr int SMEM_BYTES = OFF_YST + NYST * SZ_YST;    // the dynamic window itself is 1024-byte aligned
     static constexpr int CTAS = 1;
     static_assert(PS == 16 || PS == 8, "patch size");
     static_assert(HID % 4 == 0 && TAILQ <= 1, "hidden width: multiple of 4, at most 68");
-    static_assert(SZ_YST <= SZ_A2S, "output staging tile must fit the swizzled part of A2");
     static_assert(HI_ROWS * PS + HALO <= 128, "the rest of the body and the halo pixels must fit one M tile");
     static_assert(M1T <= 3 && M2T <= 2, "barrier slots");
     static_assert(ONE2 < 64 ? ONE2 / 4 < 16 && ONE2 >= HID : true, "constant-one channel of A2");
@@ -186,8 +188,9 @@ struct PatchWalk {
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    extern __shared__ __align__(1024) unsigned char smem_dyn[];
+    unsigned char* sm = smem_dyn;
+    if ((smem_u32(smem_dyn) & 1023u) != 0) __trap();        // the swizzled operands and the TMA boxes rely on it
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // mbarriers.  "full" = data ready for the consumer, "empty" = buffer may be overwritten by the producer.  Roles made of
@@ -206,7 +209,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
     uint64_t* hid_full = bars + 22;      // [2] hidden tile written
     uint64_t* hid_empty = bars + 24;     // [2] depthwise has consumed the hidden tile
     uint64_t* a2_full = bars + 26;       // [2] A2[k & 1] written by the depthwise warps
-    uint64_t* a2_empty = bars + 28;      // [2] A2[k & 1] free again (GEMM2 read it, the output tile staged in it has left)
+    uint64_t* a2_empty = bars + 28;      // [2] A2[k & 1] free again (GEMM2 has read it)
     uint64_t* acc2_full = bars + 30;     // GEMM2 tile in TMEM
     uint64_t* acc2_empty = bars + 31;    // epilogue 2 has drained it
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::NBAR);
@@ -342,9 +345,9 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
             const uint32_t s = it & 1, ph = (it >> 1) & 1;
             unsigned char* a1 = sm + C::OFF_A1 + s * C::SZ_A1;
             const uint32_t a1s = sm_base + C::OFF_A1 + s * C::SZ_A1, a1s_prev = sm_base + C::OFF_A1 + (s ^ 1) * C::SZ_A1;
-            // three buffers: the column saved in iteration i is read in iteration i+1, while faster warps may already be
-            // saving in iteration i+2 (the named barrier below keeps the warps within one iteration of each other)
-            const uint32_t save = sm_base + C::OFF_SAVE + (it % 3) * C::SZ_SAVE, save_prev = sm_base + C::OFF_SAVE + ((it + 2) % 3) * C::SZ_SAVE;
+            // the column saved in iteration i is read in iteration i+1; the named barrier below keeps the warps within
+            // one iteration of each other, so two buffers are enough
+            const uint32_t save = sm_base + C::OFF_SAVE + s * C::SZ_SAVE, save_prev = sm_base + C::OFF_SAVE + (s ^ 1) * C::SZ_SAVE;
             const int x0 = pw.pj * C::PS;
             const bool top = pw.pi == 0, bottom = pw.pi == p.fh - 1;
             const bool first_col = pw.pj == 0, last_col = pw.pj == p.fw - 1;
@@ -507,6 +510,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                         umma_bf16(acc, da, smem_desc(b2_addr + 2 * q * C::B2_LBO, C::B2_LBO, 128, SWZ_NONE), IDESC2, q > 0);
                     }
                     umma_commit(acc2_full);
+                    umma_commit(a2_empty + hb);            // the depthwise warps may refill A2[hb]
                 }
                 __syncwarp();
             }
@@ -594,7 +598,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
         }
         PROF_END(3, tid == 0);
     } else if (warp < C::W_DW) {
-        // =============== epilogue 2: ACC2 -> bf16 -> staging tile [c][u][v] inside the consumed A2 -> TMA store ===============
+        // =============== epilogue 2: ACC2 -> bf16 -> staging tile [c][u][v] -> TMA store ===============
         const int q = warp & 3;
         const bool is_storer = warp == C::W_EPI2 && elect_one();
         // the storer also streams the W2T | B2 part of the weight rows: stage s is free when GEMM2 of its patch has retired
@@ -612,12 +616,13 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
 #pragma unroll 1
             for (int half = 0; half < C::M2T; ++half, ++k) {
                 const uint32_t hb = k & 1;
-                PWAIT(0, acc2_full, k & 1);                // GEMM2 has retired: the accumulator is complete, A2[hb] has been read
+                PWAIT(0, acc2_full, k & 1);                // GEMM2 has retired: the accumulator is complete
                 if (is_storer && half == C::M2T - 1 && pw.patch + 2 < n1) load_w23(pw.patch + 2, it & 1);
                 tc_fence_after_sync();
                 const int pix = q * 32 + lane;              // pixel inside the half
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + C::ACC2_COL;
-                unsigned char* ydst = sm + C::OFF_A2 + hb * C::SZ_A2 + pix * 2;
+                unsigned char* yst = sm + C::OFF_YST + (C::NYST == 2 ? hb * C::SZ_YST : 0);
+                unsigned char* ydst = yst + pix * 2;
                 uint32_t v[C::N2];
 #pragma unroll
                 for (int c0 = 0; c0 < C::COUT; c0 += 16) {
@@ -639,24 +644,31 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc2_empty);    // the next GEMM2 may overwrite the accumulator
+                // the staging tile is free when the TMA store that read it last has done so: with two tiles that store was
+                // issued a half earlier and the barrier of that half already orders it; with one tile it needs its own
+                if (C::NYST == 1) {
+                    if (is_storer) {
+#ifdef HSB_IR_PROF
+                        const long long tw_ = clock64();
+#endif
+                        bulk_wait_read0();
+#ifdef HSB_IR_PROF
+                        prof_acc[1] += clock64() - tw_;
+#endif
+                    }
+                    named_bar_sync(4, 128);
+                }
                 if (pix < C::HALF_PX) {
 #pragma unroll
                     for (int c = 0; c < C::COUT; ++c)
                         *reinterpret_cast<__nv_bfloat16*>(ydst + c * C::HALF_PX * 2) = __float2bfloat16_rn(__uint_as_float(v[c]));
                 }
                 fence_proxy_async_smem();
+                if (C::NYST == 2 && is_storer) bulk_wait_read0();       // the store of the previous half has read the other tile
                 named_bar_sync(1, 128);
                 if (is_storer) {
-                    tma_store_4d(&maps.y, sm + C::OFF_A2 + hb * C::SZ_A2, pw.pj * C::PS, pw.pi * C::PS + half * C::RPH, 0, pw.b);
+                    tma_store_4d(&maps.y, yst, pw.pj * C::PS, pw.pi * C::PS + half * C::RPH, 0, pw.b);
                     bulk_commit();
-#ifdef HSB_IR_PROF
-                    const long long tw_ = clock64();
-#endif
-                    bulk_wait_read0();                     // the staging tile has been read: A2[hb] is free
-#ifdef HSB_IR_PROF
-                    prof_acc[1] += clock64() - tw_;
-#endif
-                    mbar_arrive(a2_empty + hb);
                 }
             }
         }
@@ -721,7 +733,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                     r0[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&a.x); r0[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
                     r1[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&c.x); r1[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&c.y);
                 }
-                PWAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1);       // GEMM2 and the output store of the previous use are done with A2[hb]
+                PWAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1);       // GEMM2 of the previous use is done with A2[hb]
 #pragma unroll
                 for (int u = 0; u < C::RPT; ++u) {
 #pragma unroll
