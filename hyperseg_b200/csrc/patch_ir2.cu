@@ -93,7 +93,7 @@ struct IR2 {
 #define HSB_IR_WT 4
 #endif
 #ifndef HSB_IR_RPT
-#define HSB_IR_RPT 8
+#define HSB_IR_RPT 4
 #endif
     static constexpr int WT = PS == 16 ? HSB_IR_WT : 2, STRIPS = PS / WT, RPT = PS == 16 ? HSB_IR_RPT : 4, RG = RPH / RPT, WPH = STRIPS / 2 * RG;
     static constexpr int DWMAIN = WPH * M2T, DWN = DWMAIN;
@@ -149,6 +149,15 @@ struct IR2Maps { CUtensorMap lo, lo_tail, hi, hi_tail, y; };   // x boxes of LO_
 #define PSEG_RESET() do { } while (0)
 #define PSEG(slot) do { } while (0)
 #define PROF_END(role, cond) do { } while (0)
+#endif
+// Every warp of a role polls the mbarrier itself.  The alternative -- one polling warp per role, the others parked in a named
+// barrier (-DHSB_IR_LEADERPOLL) -- removes 6000 of the 15000 warp instructions per patch (SYNCS / NANOSLEEP wake-ups) but
+// measured 3 % slower (69.4 vs 67.2 us at level 4): the kernel is bound by the shared-memory data pipe, not by issue slots,
+// and the extra barrier adds hand-off latency.
+#ifdef HSB_IR_LEADERPOLL
+#define ROLE_WAIT(slot, bar, par, leader, id, nthr) do { if (leader) PWAIT(slot, bar, par); named_bar_sync(id, nthr); } while (0)
+#else
+#define ROLE_WAIT(slot, bar, par, leader, id, nthr) PWAIT(slot, bar, par)
 #endif
 
 __device__ __forceinline__ uint32_t relu6_pack(float lo, float hi) {
@@ -266,8 +275,9 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    const int per_cta = (p.total + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int n0 = (int)blockIdx.x * per_cta, n1 = min(n0 + per_cta, p.total);     // this CTA's run of patches
+    // this CTA's run of patches: balanced split (run lengths differ by at most one; grid <= total, so no run is empty)
+    const int n0 = (int)((long long)blockIdx.x * p.total / (int)gridDim.x);
+    const int n1 = (int)((long long)(blockIdx.x + 1) * p.total / (int)gridDim.x);
     PatchWalk pw;
     pw.init(n0, p.fh, p.fw);
 
@@ -370,7 +380,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
             const uint32_t dst_base = role == 0 ? save : a1s_prev;
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
-                if (pass == 0) PWAIT(0, lo_full + s, ph); else PWAIT(1, hi_full + s, ph);      // that part of the tile has landed
+                if (pass == 0) ROLE_WAIT(0, lo_full + s, ph, ptid < 32, 7, PT); else ROLE_WAIT(1, hi_full + s, ph, ptid < 32, 7, PT);      // that part of the tile has landed
                 // mirror rows (whole M-groups): tile row 0 <- row 2 (pass A), row TH-1 <- row TH-3 (the pass that owns row TH-1)
                 const bool do_top = top && pass == 0, do_bottom = bottom && pass == (C::HI_ROWS > 0 ? 1 : 0);
                 if (do_top || do_bottom) {
@@ -522,13 +532,14 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
         PROF_BEGIN();
         for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
             const uint32_t s = it & 1, ph = (it >> 1) & 1;
-            PWAIT(0, hid_empty + s, ph ^ 1);
+            ROLE_WAIT(0, hid_empty + s, ph ^ 1, warp == C::W_EPI1, 5, 128);
             unsigned char* hid = sm + C::OFF_HID + s * C::SZ_HID;
 #pragma unroll 1
             for (int t = 0; t < C::M1T; ++t) {
                 // M row -> pixel of the TH x TH hidden tile (-1: a row nobody needs)
                 const int ml = q * 32 + lane;
                 int hpix = -1;
+                ROLE_WAIT(1 + t, acc1_full + s * 3 + t, ph, warp == C::W_EPI1, 5, 128);
                 if (t < C::NBT) {
                     const int m = t * 128 + ml;
                     if (m < C::LO_ROWS * C::PS) hpix = (m / C::PS) * C::TH + (m % C::PS) + 1;
@@ -541,7 +552,6 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                     }
                     if (q * 32 >= C::HI_ROWS * C::PS + C::HALO) continue;
                 }
-                PWAIT(1 + t, acc1_full + s * 3 + t, ph);
                 tc_fence_after_sync();
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + s * C::ACC1_COLS + t * C::N1;
                 unsigned char* hrow = hid + (size_t)(hpix < 0 ? 0 : hpix) * C::HPITCH;
@@ -607,7 +617,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
             bulk_g2s(sm + C::OFF_W23 + s * C::SZ_W23, p.w + (size_t)patch * p.w_row_stride + C::SZ_B1 / 2, C::SZ_W2T + C::SZ_B2, w23_full + s);
         };
         if (is_storer) {
-            load_w23(n0, 0);
+            if (n0 < n1) load_w23(n0, 0);
             if (n0 + 1 < n1) load_w23(n0 + 1, 1);
         }
         uint32_t k = 0;
@@ -616,7 +626,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
 #pragma unroll 1
             for (int half = 0; half < C::M2T; ++half, ++k) {
                 const uint32_t hb = k & 1;
-                PWAIT(0, acc2_full, k & 1);                // GEMM2 has retired: the accumulator is complete
+                ROLE_WAIT(0, acc2_full, k & 1, warp == C::W_EPI2, 6, 128);       // GEMM2 has retired: the accumulator is complete
                 if (is_storer && half == C::M2T - 1 && pw.patch + 2 < n1) load_w23(pw.patch + 2, it & 1);
                 tc_fence_after_sync();
                 const int pix = q * 32 + lane;              // pixel inside the half
@@ -708,7 +718,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
             const unsigned char* wbuf = sm + C::OFF_W23 + s * C::SZ_W23;
             const unsigned char* hid = sm + C::OFF_HID + s * C::SZ_HID;
             unsigned char* dst = sm + C::OFF_A2 + hb * C::SZ_A2;
-            PWAIT(0, w23_full + s, ph);
+            ROLE_WAIT(0, w23_full + s, ph, dw == 0, 8, 32 * C::DWN);
             __nv_bfloat162 wt[9][2], bias[2];
             if (active) {
 #pragma unroll
@@ -721,7 +731,9 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                 bias[0] = *reinterpret_cast<const __nv_bfloat162*>(&t2.x);
                 bias[1] = *reinterpret_cast<const __nv_bfloat162*>(&t2.y);
             }
-            PWAIT(1, hid_full + s, ph);
+            ROLE_WAIT(1, hid_full + s, ph, dw == 0, 8, 32 * C::DWN);
+            // GEMM2 of the previous use is done with A2[hb]: one poller per half
+            ROLE_WAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1, dw % C::WPH == 0, 9 + my_half, 32 * C::WPH);
             if (active) {
                 const int u0 = my_half * C::RPH + lr0;      // first output row = first tile row of the window
                 const unsigned char* src = hid + (size_t)(u0 * C::TH + c0) * C::HPITCH + quad * 8;
@@ -733,7 +745,6 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                     r0[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&a.x); r0[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
                     r1[j][0] = *reinterpret_cast<const __nv_bfloat162*>(&c.x); r1[j][1] = *reinterpret_cast<const __nv_bfloat162*>(&c.y);
                 }
-                PWAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1);       // GEMM2 of the previous use is done with A2[hb]
 #pragma unroll
                 for (int u = 0; u < C::RPT; ++u) {
 #pragma unroll
@@ -763,14 +774,12 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                     for (int j = 0; j < C::WT + 2; ++j) { r0[j][0] = r1[j][0]; r0[j][1] = r1[j][1]; r1[j][0] = r2[j][0]; r1[j][1] = r2[j][1]; }
                 }
             } else if (ones_lane) {
-                PWAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1);
 #pragma unroll
                 for (int u = 0; u < C::RPT; ++u)
 #pragma unroll
                     for (int j = 0; j < C::WT; ++j) *reinterpret_cast<uint2*>(dst + dst_off[j] + u * dst_row) = make_uint2(0x00003F80u, 0u);
             }
             if (tail_lane) {                                // pixels of channels 64..67 (quad 16): weights are broadcast loads
-                if (!active && !ones_lane) PWAIT(2, a2_empty + hb, ((kk >> 1) & 1) ^ 1);
                 constexpr int TW = TAIL_PER % 2 == 0 ? 2 : 1;    // pixels per step: horizontally adjacent pairs share their window columns
                 const uint2 bq = *reinterpret_cast<const uint2*>(sm + C::OFF_B2B + 16 * 8);
                 __nv_bfloat162 wq[9][2];

@@ -481,9 +481,11 @@ def test_ir_arranged_kernel_every_border_case(shape, grid):
     assert rel_err(_run_arranged(x, w, hid, Cout, bns).float().cpu(), ref) < IR2_TOL
 
 
-@pytest.mark.parametrize("shape,grid", [((34, 68, 19, 16), (2, 16, 24)), ((24, 48, 16, 8), (4, 16, 24)), ((26, 52, 19, 16), (1, 13, 12))])
+@pytest.mark.parametrize("shape,grid", [((34, 68, 19, 16), (2, 16, 24)), ((24, 48, 16, 8), (4, 16, 24)), ((26, 52, 19, 16), (1, 13, 12)),
+                                        ((24, 48, 16, 8), (3, 16, 32)), ((14, 28, 8, 8), (1, 15, 31))])
 def test_ir_arranged_kernel_long_runs(shape, grid):
-    """More patches than CTAs: several patches per CTA, runs that wrap around rows and images, both weight layouts."""
+    """More patches than CTAs: several patches per CTA, runs that wrap around rows and images, both weight layouts; patch
+    counts that do not divide by the SM count (1536 = 148 x 10.4: runs of 10 and 11 patches, none empty)."""
     Cin, hid, Cout, ps = shape
     B, fh, fw = grid
     hp = Cin * hid + 9 * hid + hid * Cout
