@@ -60,6 +60,33 @@ __host__ __device__ inline size_t head_smem_bytes_arranged(int sig_pad, int kpad
     return (size_t)sig_pad * HD_M * 2 + 2 * (size_t)nt * kpad_max * 2 + (size_t)HD_M * (nt * 2 + 16) + 128 + 1024;
 }
 
+// Staged rows -> global rows, one warp: 32 rows x up to HC columns.  A lane moves one vector of sizeof(V) / 2 columns; the
+// lanes that cover one row's HC columns sit next to each other, so an instruction writes whole contiguous row segments.
+// Columns past nvalid are not written (a vector that straddles nvalid falls back to single elements).
+template <typename V, int HC>
+__device__ __forceinline__ void head_copy_out(const unsigned char* sbase, int spitch, __nv_bfloat16* dbase, int64_t row_stride,
+                                              int nrows, int nvalid, int lane) {
+    constexpr int VC = sizeof(V) / 2;                       // columns per vector
+    constexpr int LPR = HC / VC < 32 ? HC / VC : 32;        // lanes per row
+    constexpr int RPI = 32 / LPR;                           // rows per instruction
+    constexpr int CPI = LPR * VC;                           // columns per instruction and row
+    const int lr = lane / LPR, lc = (lane % LPR) * VC;
+#pragma unroll
+    for (int c0 = 0; c0 < HC; c0 += CPI) {
+        const int c = c0 + lc;
+        if (c >= nvalid) continue;
+        const bool whole = c + VC <= nvalid;
+        const unsigned char* sp = sbase + (size_t)lr * spitch + c * 2;
+        __nv_bfloat16* dp = dbase + (size_t)lr * row_stride + c;
+#pragma unroll 4
+        for (int r = lr; r < nrows; r += RPI, sp += RPI * spitch, dp += RPI * row_stride) {
+            if (whole) *reinterpret_cast<V*>(dp) = *reinterpret_cast<const V*>(sp);
+            else
+                for (int e = 0; e < nvalid - c; ++e) dp[e] = reinterpret_cast<const __nv_bfloat16*>(sp)[e];
+        }
+    }
+}
+
 // A CTA owns 128 positions and a contiguous range of (group, channel-tile) items.  Warp 8 is the producer: it copies
 // the item's signal slab into the MN-major A operand (all 32 lanes), streams the packed B tile with cp.async.bulk and
 // issues the MMAs (lane 0) into a two-stage TMEM accumulator.  Warps 0-7 drain: quadrant = warp % 4, column half =
@@ -104,24 +131,28 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
         // the head's whole signal slice for these 128 positions, MN-major: unit(mc, k) = (k/8)*LBO + mc*128 + (k%8)*16 holds
         // 8 consecutive positions of channel sig_first + k (sig_first = slice start rounded down to 8); channels outside
         // the slice are zero (their packed weights are zero as well)
-        const int sig_first = p.sig_index & ~7, units = p.kpad * (HD_M / 8);
-        for (int base = 0; base < units; base += HD_THREADS * 4) {
+        const int sig_first = p.sig_index & ~7;
+        // thread = (8-position unit mc, channel k0 + 18 j): the position arithmetic is done once per thread and the 16
+        // lanes of a half-warp read 256 contiguous bytes of one channel
+        constexpr int KSTEP = HD_THREADS / (HD_M / 8);
+        const int mc = tid % (HD_M / 8), n = n0 + mc * 8;
+        const bool in_range = n < p.NTOT;
+        const int bimg = in_range ? n / p.P : 0, pp = in_range ? n % p.P : 0;      // P % 8 == 0: a unit never straddles images
+        const __nv_bfloat16* sbase = p.s + (size_t)bimg * p.ssb + pp;
+        unsigned char* abase = a_sm + mc * 128;
+        for (int kb = tid / (HD_M / 8); kb < p.kpad; kb += 4 * KSTEP) {
             uint4 v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int i = base + e * HD_THREADS + tid;
-                const int mc = i % (HD_M / 8), k = i / (HD_M / 8), ch = sig_first + k, n = n0 + mc * 8;
+                const int k = kb + e * KSTEP, ch = sig_first + k;
                 v[e] = make_uint4(0, 0, 0, 0);
-                if (i < units && ch >= p.sig_index && ch < p.sig_end && n < p.NTOT) {
-                    const int b = n / p.P, pp = n % p.P;              // P % 8 == 0: a unit never straddles images
-                    v[e] = __ldg(reinterpret_cast<const uint4*>(p.s + (size_t)b * p.ssb + (size_t)ch * p.ssc + pp));
-                }
+                if (k < p.kpad && in_range && ch >= p.sig_index && ch < p.sig_end)
+                    v[e] = __ldg(reinterpret_cast<const uint4*>(sbase + (size_t)ch * p.ssc));
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int i = base + e * HD_THREADS + tid;
-                const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
-                if (i < units) *reinterpret_cast<uint4*>(a_sm + (k >> 3) * ((HD_M / 8) * 128) + mc * 128 + (k & 7) * 16) = v[e];
+                const int k = kb + e * KSTEP;
+                if (k < p.kpad) *reinterpret_cast<uint4*>(abase + (k >> 3) * ((HD_M / 8) * 128) + (k & 7) * 16) = v[e];
             }
         }
         fence_proxy_async_smem();
@@ -149,25 +180,23 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             if (!ARR && (st ? stage_group1 : stage_group0) != g) {
                 unsigned char* a_dst = a_sm + st * a_bytes;
                 // unit(mc, k) = (k/8)*LBO + mc*128 + (k%8)*16: 8 consecutive positions of signal channel k
-                const int units = k_item * (HD_M / 8);
-                for (int base = 0; base < units; base += 32 * 8) {      // 8 independent 16-byte loads in flight per lane
+                // lane = (8-position unit mc = lane % 16, channel parity): position arithmetic once per lane
+                const int mc = lane & (HD_M / 8 - 1), n = n0 + mc * 8;
+                const bool in_range = n < p.NTOT;
+                const int bimg = in_range ? n / p.P : 0, pp = in_range ? n % p.P : 0;   // P % 8 == 0: a unit never straddles images
+                const __nv_bfloat16* sbase = p.s + (size_t)bimg * p.ssb + (size_t)k_first * p.ssc + pp;
+                for (int kb = lane >> 4; kb < k_item; kb += 16) {       // 8 independent 16-byte loads in flight per lane
                     uint4 v[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const int i = base + e * 32 + lane;
-                        const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
-                        const int n = n0 + mc * 8;
+                        const int k = kb + 2 * e;
                         v[e] = make_uint4(0, 0, 0, 0);
-                        if (i < units && k < k_count && n < p.NTOT) {
-                            const int b = n / p.P, pp = n % p.P;          // P % 8 == 0: a unit never straddles images
-                            v[e] = __ldg(reinterpret_cast<const uint4*>(p.s + (size_t)b * p.ssb + (size_t)(k_first + k) * p.ssc + pp));
-                        }
+                        if (k < k_count && in_range) v[e] = __ldg(reinterpret_cast<const uint4*>(sbase + (size_t)k * p.ssc));
                     }
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const int i = base + e * 32 + lane;
-                        const int mc = i % (HD_M / 8), k = i / (HD_M / 8);
-                        if (i < units) *reinterpret_cast<uint4*>(a_dst + (k >> 3) * a_lbo + mc * 128 + (k & 7) * 16) = v[e];
+                        const int k = kb + 2 * e;
+                        if (k < k_item) *reinterpret_cast<uint4*>(a_dst + (k >> 3) * a_lbo + mc * 128 + (k & 7) * 16) = v[e];
                     }
                 }
                 if (st) stage_group1 = g; else stage_group0 = g;
@@ -247,37 +276,19 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(d_empty + st);          // TMEM stage free again
-            // coalesced write-out of this warp's 32 rows x its column half
+            // coalesced write-out of this warp's 32 rows x its column half: V columns per lane, 2 HC / (64 V)... rows per
+            // instruction (16-byte lanes: 4 rows of 128 contiguous bytes each); V = the widest vector the start column allows
             if (nvalid > 0) {
                 const int ob = o_base + half * HC;
-                const bool pairs = (ob & 1) == 0;
                 const int nrows = min(32, p.NTOT - (n0 + q * 32));
                 const unsigned char* sbase = st_sm + (size_t)(q * 32) * STAGE_PITCH + half * HC * 2;
                 __nv_bfloat16* dbase = p.out + (size_t)(n0 + q * 32) * p.row_stride + ob;
-                if (pairs) {
-                    // lane = column pair, rows unrolled: 8 independent shared loads / global stores in flight;
-                    // for a fixed row the 32 lanes write 128 contiguous bytes
-                    for (int c = lane * 2; c < nvalid; c += 64) {
-                        const bool two = c + 1 < nvalid;
-#pragma unroll 8
-                        for (int r = 0; r < 32; ++r) {
-                            if (r < nrows) {
-                                const unsigned char* sp = sbase + (size_t)r * STAGE_PITCH + c * 2;
-                                __nv_bfloat16* dp = dbase + (size_t)r * p.row_stride + c;
-                                if (two) *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
-                                else *dp = *reinterpret_cast<const __nv_bfloat16*>(sp);
-                            }
-                        }
-                    }
-                } else {
-                    for (int c = lane; c < nvalid; c += 32) {
-#pragma unroll 8
-                        for (int r = 0; r < 32; ++r)
-                            if (r < nrows)
-                                dbase[(size_t)r * p.row_stride + c] =
-                                    *reinterpret_cast<const __nv_bfloat16*>(sbase + (size_t)r * STAGE_PITCH + c * 2);
-                    }
-                }
+                const bool row16 = (p.row_stride & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+                if (row16 && (ob & 7) == 0) head_copy_out<uint4, HC>(sbase, STAGE_PITCH, dbase, p.row_stride, nrows, nvalid, lane);
+                else if (row16 && (ob & 3) == 0) head_copy_out<uint2, HC>(sbase, STAGE_PITCH, dbase, p.row_stride, nrows, nvalid, lane);
+                else if ((p.row_stride & 1) == 0 && (ob & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 3) == 0)
+                    head_copy_out<uint32_t, HC>(sbase, STAGE_PITCH, dbase, p.row_stride, nrows, nvalid, lane);
+                else head_copy_out<unsigned short, HC>(sbase, STAGE_PITCH, dbase, p.row_stride, nrows, nvalid, lane);
             }
             __syncwarp();       // staging rows are rewritten by the next item
         }
