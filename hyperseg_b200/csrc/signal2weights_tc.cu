@@ -31,6 +31,8 @@ constexpr int HD_M = 128;                  // positions per CTA
 constexpr int HD_EPI_WARPS = 8;            // 4 TMEM quadrants x 2 column halves
 constexpr int HD_THREADS = 32 * (HD_EPI_WARPS + 1);     // + 1 producer / MMA warp
 constexpr int HD_STAGE_PITCH = HD_NT * 2 + 16;
+constexpr int HD_TBL_ITEMS = 64;           // item table entries of one CTA kept in shared memory
+constexpr int HD_TBL_BYTES = HD_TBL_ITEMS * 16 + (HD_M / 8) * 8;     // + first-element offsets of the 16 position units
 
 struct HeadTCParams {
     const __nv_bfloat16* s;
@@ -52,12 +54,12 @@ __host__ __device__ inline size_t head_smem_bytes(int kpad, int nt = HD_NT) {
     size_t a = 2 * (size_t)kpad * HD_M * 2;             // two A stages (signal slab of the item's group)
     size_t b = 2 * (size_t)nt * kpad * 2;               // two B stages
     size_t st = (size_t)HD_M * (nt * 2 + 16);           // output staging
-    return a + b + st + 128 + 1024;
+    return a + b + st + 128 + HD_TBL_BYTES + 1024;
 }
 
 // arranged mode: the whole signal slice of the head stays resident (one MN-major slab, k-chunks addressed per item)
 __host__ __device__ inline size_t head_smem_bytes_arranged(int sig_pad, int kpad_max, int nt) {
-    return (size_t)sig_pad * HD_M * 2 + 2 * (size_t)nt * kpad_max * 2 + (size_t)HD_M * (nt * 2 + 16) + 128 + 1024;
+    return (size_t)sig_pad * HD_M * 2 + 2 * (size_t)nt * kpad_max * 2 + (size_t)HD_M * (nt * 2 + 16) + 128 + HD_TBL_BYTES + 1024;
 }
 
 // Staged rows -> global rows, one warp: 32 rows x up to HC columns.  A lane moves one vector of sizeof(V) / 2 columns; the
@@ -78,7 +80,14 @@ __device__ __forceinline__ void head_copy_out(const unsigned char* sbase, int sp
         const bool whole = c + VC <= nvalid;
         const unsigned char* sp = sbase + (size_t)lr * spitch + c * 2;
         __nv_bfloat16* dp = dbase + (size_t)lr * row_stride + c;
-#pragma unroll 4
+        if (whole && nrows == 32) {                              // the common case: all loads in flight, then all stores
+            V v[32 / RPI];
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i) v[i] = *reinterpret_cast<const V*>(sp + (size_t)i * RPI * spitch);
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i) *reinterpret_cast<V*>(dp + (size_t)i * RPI * row_stride) = v[i];
+            continue;
+        }
         for (int r = lr; r < nrows; r += RPI, sp += RPI * spitch, dp += RPI * row_stride) {
             if (whole) *reinterpret_cast<V*>(dp) = *reinterpret_cast<const V*>(sp);
             else
@@ -110,6 +119,8 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
     uint64_t* d_full = bars + 4;      // [2] accumulator ready
     uint64_t* d_empty = bars + 6;     // [2] accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    int4* tbl_sm = reinterpret_cast<int4*>(bars + 16);                          // arranged mode: this CTA's items
+    int64_t* pos_sm = reinterpret_cast<int64_t*>(tbl_sm + HD_TBL_ITEMS);        // element offset of each 8-position unit (-1: past the end)
 
     const int n0 = blockIdx.x * HD_M;
     const int per = (p.items + p.splits - 1) / p.splits;
@@ -132,27 +143,31 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
         // 8 consecutive positions of channel sig_first + k (sig_first = slice start rounded down to 8); channels outside
         // the slice are zero (their packed weights are zero as well)
         const int sig_first = p.sig_index & ~7;
-        // thread = (8-position unit mc, channel k0 + 18 j): the position arithmetic is done once per thread and the 16
-        // lanes of a half-warp read 256 contiguous bytes of one channel
-        constexpr int KSTEP = HD_THREADS / (HD_M / 8);
-        const int mc = tid % (HD_M / 8), n = n0 + mc * 8;
-        const bool in_range = n < p.NTOT;
-        const int bimg = in_range ? n / p.P : 0, pp = in_range ? n % p.P : 0;      // P % 8 == 0: a unit never straddles images
-        const __nv_bfloat16* sbase = p.s + (size_t)bimg * p.ssb + pp;
-        unsigned char* abase = a_sm + mc * 128;
-        for (int kb = tid / (HD_M / 8); kb < p.kpad; kb += 4 * KSTEP) {
+        if (tid < HD_M / 8) {
+            const int n = n0 + tid * 8;                                   // P % 8 == 0: a unit never straddles images
+            pos_sm[tid] = n < p.NTOT ? (int64_t)(n / p.P) * p.ssb + n % p.P : -1;
+        }
+        for (int j = tid; j < min(nitems, HD_TBL_ITEMS); j += HD_THREADS) tbl_sm[j] = __ldg(p.table + it0 + j);
+        __syncthreads();
+        // 16-byte chunk L of the slab = (k / 8, mc, k % 8): consecutive threads write consecutive chunks (conflict-free) and
+        // read, per channel, 64 contiguous bytes (4 position units)
+        const int chunks = p.kpad * (HD_M / 8);
+        for (int base = 0; base < chunks; base += 4 * HD_THREADS) {
             uint4 v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int k = kb + e * KSTEP, ch = sig_first + k;
+                const int L = base + e * HD_THREADS + tid;
+                const int k = (L >> 7) * 8 + (L & 7), mc = (L >> 3) & (HD_M / 8 - 1), ch = sig_first + k;
                 v[e] = make_uint4(0, 0, 0, 0);
-                if (k < p.kpad && in_range && ch >= p.sig_index && ch < p.sig_end)
-                    v[e] = __ldg(reinterpret_cast<const uint4*>(sbase + (size_t)ch * p.ssc));
+                if (L < chunks && ch >= p.sig_index && ch < p.sig_end) {
+                    const int64_t off = pos_sm[mc];
+                    if (off >= 0) v[e] = __ldg(reinterpret_cast<const uint4*>(p.s + off + (size_t)ch * p.ssc));
+                }
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int k = kb + e * KSTEP;
-                if (k < p.kpad) *reinterpret_cast<uint4*>(abase + (k >> 3) * ((HD_M / 8) * 128) + (k & 7) * 16) = v[e];
+                const int L = base + e * HD_THREADS + tid;
+                if (L < chunks) *reinterpret_cast<uint4*>(a_sm + (size_t)L * 16) = v[e];
             }
         }
         fence_proxy_async_smem();
@@ -171,7 +186,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             const int st = j & 1, it = it0 + j;
             int g, t, k_first, k_count, k_item;      // slab id, tile, first signal channel, channels to copy, item's padded K
             if (ARR) {
-                const int4 e = __ldg(p.table + it);
+                const int4 e = j < HD_TBL_ITEMS ? tbl_sm[j] : __ldg(p.table + it);
                 g = e.x * 4096 + e.y; t = 0; k_first = e.x; k_item = e.y; k_count = max(0, min(e.y, p.sig_end - e.x));
             } else {
                 g = it / p.otiles; t = it % p.otiles; k_first = p.sig_index + g * p.spg; k_count = p.spg; k_item = kpad;
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                 if (j >= 2) mbar_wait(d_empty + st, ((j >> 1) - 1) & 1);      // epilogue drained this accumulator
                 tc_fence_after_sync();
                 // arranged: the item's first channel (a multiple of 8 past the slab's first) selects the k-chunk of the resident slab
-                const int4 te = ARR ? __ldg(p.table + it0 + j) : make_int4(0, kpad, 0, 0);
+                const int4 te = ARR ? (j < HD_TBL_ITEMS ? tbl_sm[j] : __ldg(p.table + it0 + j)) : make_int4(0, kpad, 0, 0);
                 const uint32_t a_addr = ARR ? smem_u32(a_sm) + ((te.x - (p.sig_index & ~7)) >> 3) * a_lbo : smem_u32(a_sm + st * a_bytes);
                 const uint32_t b_addr = smem_u32(b_sm + st * b_bytes);
                 const int ksteps = te.y / 16;
@@ -242,7 +257,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             const int st = j & 1, it = it0 + j;
             int o_base, o_end;
             if (ARR) {
-                const int4 e = __ldg(p.table + it);
+                const int4 e = j < HD_TBL_ITEMS ? tbl_sm[j] : __ldg(p.table + it);
                 o_base = e.z; o_end = e.z + e.w;
             } else {
                 const int g = it / p.otiles, t = it % p.otiles;
@@ -419,7 +434,7 @@ static bool plan_arranged(int sig_index, int sig_ch, int out_ch, int groups, int
     // the signal slice stays resident (padded: first channel rounded down to 8, + 16 so that a tile's padded range never
     // leaves the slab); what is left of the shared memory holds two stages of packed weights
     pl->sig_pad = ((sig_index & 7) + sig_ch + 15) / 16 * 16 + 16;
-    const long budget = 227L * 1024 - (long)pl->sig_pad * HD_M * 2 - (long)HD_M * (HD_NT_ARR * 2 + 16) - 2048;
+    const long budget = 227L * 1024 - (long)pl->sig_pad * HD_M * 2 - (long)HD_M * (HD_NT_ARR * 2 + 16) - 2048 - HD_TBL_BYTES;
     const int KLIM = (int)std::min<long>(256, budget / (2 * HD_NT_ARR * 2) / 16 * 16);
     if (KLIM < 16) return false;
     int c0 = 0, gmin = groups, gmax = -1;
