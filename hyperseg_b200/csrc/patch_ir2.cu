@@ -65,7 +65,13 @@ struct IR2 {
     static constexpr int GPT = 128 / PS;                       // M-groups per 128-row tile
     // M tiles of GEMM1: NBT tiles of body rows [0, LO_ROWS), then one tile that starts at group LO_ROWS and holds the
     // remaining HI_ROWS body rows and the halo groups.  The body tiles do not depend on the neighbours' tiles.
-    static constexpr int LO_ROWS = PS == 16 ? 16 : TH, HI_ROWS = TH - LO_ROWS;
+    // 8x8 patches: one body tile (80 pixels) + one halo tile (20 pixels).  -DHSB_IR_LO8=0 makes the whole halo tile ONE M tile
+    // (half the GEMM1 / epilogue-1 passes, but GEMM1 then waits for the neighbour's column): measured slower in back-to-back
+    // launches (37.3 vs 30.8 us at level 3), so the split form stays.
+#ifndef HSB_IR_LO8
+#define HSB_IR_LO8 10
+#endif
+    static constexpr int LO_ROWS = PS == 16 ? 16 : HSB_IR_LO8, HI_ROWS = TH - LO_ROWS;
     static constexpr int NBT = (LO_ROWS * PS + 127) / 128, M1T = NBT + 1;
     static constexpr int T = TH * TH;                          // pixels of the halo tile
     static constexpr int SZ_A1 = ir_r1024((K1 / 8 - 1) * A1_KGS + (LO_ROWS + GPT) * GRP);     // incl. what the last tile over-reads
@@ -309,7 +315,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
         //     the stage, destination inside the save buffer (even lanes) or inside the other stage (odd lanes).
         const int role = ptid & 1, pair = ptid >> 1;
         constexpr int NT_LO = (NE_LO + PT / 2 - 1) / (PT / 2), NT_HI = (NE_HI + PT / 2 - 1) / (PT / 2);
-        uint32_t t_lo[NT_LO], t_hi[NT_HI > 0 ? NT_HI : 1];     // src | dst << 16; dst 0xFFFF = no task (reads offset 0, stores nothing)
+        uint32_t t_lo[NT_LO > 0 ? NT_LO : 1], t_hi[NT_HI > 0 ? NT_HI : 1];     // src | dst << 16; dst 0xFFFF = no task (reads offset 0, stores nothing)
         auto make_task = [&](int e) {
             const uint32_t src = swz(body_off(e) + 2 * (role == 0 ? C::PS - 1 : 0));
             const uint32_t dst = role == 0 ? (uint32_t)(2 * e) : slot_off(e, 1);
@@ -382,7 +388,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
             for (int pass = 0; pass < 2; ++pass) {
                 if (pass == 0) ROLE_WAIT(0, lo_full + s, ph, ptid < 32, 7, PT); else ROLE_WAIT(1, hi_full + s, ph, ptid < 32, 7, PT);      // that part of the tile has landed
                 // mirror rows (whole M-groups): tile row 0 <- row 2 (pass A), row TH-1 <- row TH-3 (the pass that owns row TH-1)
-                const bool do_top = top && pass == 0, do_bottom = bottom && pass == (C::HI_ROWS > 0 ? 1 : 0);
+                const bool do_top = top && pass == (C::LO_ROWS > 0 ? 0 : 1), do_bottom = bottom && pass == (C::HI_ROWS > 0 ? 1 : 0);
                 if (do_top || do_bottom) {
                     for (int i = ptid; i < C::KC1 * (C::GRP / 16); i += PT) {
                         unsigned char* base = a1 + (i / (C::GRP / 16)) * C::A1_KGS + (i % (C::GRP / 16)) * 16;
@@ -392,14 +398,14 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
                     named_bar_sync(2, PT);                 // the column copies below read the mirrored rows
                 }
                 if (copy_on) {
-                    if (pass == 0) {
-                        unsigned short v[NT_LO];
+                    if (pass == 0 && C::LO_ROWS > 0) {
+                        unsigned short v[NT_LO > 0 ? NT_LO : 1];
 #pragma unroll
                         for (int j = 0; j < NT_LO; ++j) v[j] = lds16(a1s + (t_lo[j] & 0xFFFFu));       // a missing task reads a valid (unused) address
 #pragma unroll
                         for (int j = 0; j < NT_LO; ++j)
                             if (j < NT_LO - 1 || (t_lo[j] >> 16) != 0xFFFFu) sts16(dst_base + (t_lo[j] >> 16), v[j]);
-                    } else if (C::HI_ROWS > 0) {
+                    } else if (pass == 1 && C::HI_ROWS > 0) {
                         unsigned short v[NT_HI > 0 ? NT_HI : 1];
 #pragma unroll
                         for (int j = 0; j < NT_HI; ++j) v[j] = lds16(a1s + (t_hi[j] & 0xFFFFu));
@@ -436,7 +442,7 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
             if (elect_one()) {
                 mbar_arrive_expect_tx(lo_full + s, C::KC1 * C::LO_ROWS * C::GRP);
 #pragma unroll
-                for (int kg = 0; kg < C::KC1; ++kg) {
+                for (int kg = 0; kg < (C::LO_ROWS > 0 ? C::KC1 : 0); ++kg) {
                     const bool tail = (C::CIN % 8 != 0) && kg == C::KC1 - 1;
                     tma_load_5d(a1 + kg * C::A1_KGS, tail ? &maps.lo_tail : &maps.lo, x0, 0, y0, tail ? 0 : kg, pw.b, lo_full + s);
                 }
@@ -901,7 +907,7 @@ static int launch_ir2(const void* x, void* y, const IR2Params& p, cudaStream_t s
             *tail = *full;
         }
     };
-    make_x(&maps.lo, &maps.lo_tail, C::LO_ROWS);
+    make_x(&maps.lo, &maps.lo_tail, C::LO_ROWS > 0 ? C::LO_ROWS : 1);
     make_x(&maps.hi, &maps.hi_tail, C::HI_ROWS > 0 ? C::HI_ROWS : 1);
     if (r == CUDA_SUCCESS) {
         const cuuint64_t ydim[4] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)C::COUT, (cuuint64_t)p.B};

@@ -48,6 +48,7 @@ struct HeadTCParams {
     int kpad_max, sig_end;            // arranged mode: operand stages are sized for kpad_max; signal channels >= sig_end read as 0
     int64_t ssb, ssc;                 // signal strides (elements); position stride is 1
     int64_t row_stride;               // output row stride (elements)
+    long long* prof;                  // profiling build (-DHSB_HEAD_PROF): 8 counters per CTA
 };
 
 __host__ __device__ inline size_t head_smem_bytes(int kpad, int nt = HD_NT) {
@@ -107,6 +108,10 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
     // align by pointer arithmetic on the __shared__ array so the compiler keeps the address space (LDS/STS, not generic)
     unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef HSB_HEAD_PROF
+    const long long prof_t0 = clock64();
+    long long prof_wait = 0, prof_ld = 0, prof_copy = 0, prof_pro = 0, prof_mma_wait = 0;
+#endif
     const int kpad = ARR ? p.kpad_max : p.kpad;             // operand stage size; an arranged item may use less
     // arranged mode: one resident A slab (p.kpad = padded width of the head's signal slice) instead of two stages
     const size_t a_bytes = (size_t)(ARR ? p.kpad : kpad) * HD_M * 2, b_bytes = (size_t)NT * kpad * 2;
@@ -149,13 +154,29 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
         }
         for (int j = tid; j < min(nitems, HD_TBL_ITEMS); j += HD_THREADS) tbl_sm[j] = __ldg(p.table + it0 + j);
         __syncthreads();
+        // the packed weights of the first two items do not depend on the slab: their copies fly while it is staged
+        if (tid == HD_EPI_WARPS * 32) {
+            for (int j = 0; j < min(nitems, 2); ++j) {
+                const uint32_t bytes = (uint32_t)((size_t)NT * tbl_sm[j].y * 2);
+                mbar_arrive_expect_tx(b_full + j, bytes);
+                bulk_g2s(b_sm + j * b_bytes, p.packed + (size_t)(it0 + j) * NT * kpad, bytes, b_full + j);
+            }
+        }
         // 16-byte chunk L of the slab = (k / 8, mc, k % 8): consecutive threads write consecutive chunks (conflict-free) and
         // read, per channel, 64 contiguous bytes (4 position units)
-        const int chunks = p.kpad * (HD_M / 8);
-        for (int base = 0; base < chunks; base += 4 * HD_THREADS) {
-            uint4 v[4];
+        // only the 8-channel groups this CTA's items read (a CTA holds a quarter or so of the row's tiles)
+        int kg_lo = 0, kg_hi = p.kpad / 8;
+        if (nitems <= HD_TBL_ITEMS) {
+            int lo = 1 << 30, hi = 0;
+            for (int j = 0; j < nitems; ++j) { const int4 e = tbl_sm[j]; lo = min(lo, e.x); hi = max(hi, e.x + e.y); }
+            kg_lo = max(0, (lo - sig_first) >> 3); kg_hi = min(kg_hi, (hi - sig_first + 7) >> 3);
+        }
+        const int chunk0 = kg_lo * HD_M, chunks = kg_hi * HD_M;       // 128 chunks (16 units x 8 channels) per group
+        constexpr int DEPTH = 10;                  // 16-byte loads in flight per thread
+        for (int base = chunk0; base < chunks; base += DEPTH * HD_THREADS) {
+            uint4 v[DEPTH];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < DEPTH; ++e) {
                 const int L = base + e * HD_THREADS + tid;
                 const int k = (L >> 7) * 8 + (L & 7), mc = (L >> 3) & (HD_M / 8 - 1), ch = sig_first + k;
                 v[e] = make_uint4(0, 0, 0, 0);
@@ -165,7 +186,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < DEPTH; ++e) {
                 const int L = base + e * HD_THREADS + tid;
                 if (L < chunks) *reinterpret_cast<uint4*>(a_sm + (size_t)L * 16) = v[e];
             }
@@ -176,6 +197,9 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+#ifdef HSB_HEAD_PROF
+    prof_pro = clock64() - prof_t0;
+#endif
     const int a_lbo = (HD_M / 8) * 128, b_lbo = (NT / 8) * 128;
 
     if (warp == HD_EPI_WARPS) {
@@ -218,10 +242,14 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                 fence_proxy_async_smem();
             }
             __syncwarp();
-            if (elect_one()) {
+            if ((!ARR || j >= 2) && elect_one()) {            // arranged: items 0 and 1 were requested before the slab was staged
                 const uint32_t bytes = (uint32_t)((size_t)NT * k_item * 2);
+#ifdef HSB_HEAD_NOLOAD      // timing experiment only (wrong results): how much of the item period is the weight-tile copy?
+                (void)bytes; mbar_arrive(b_full + st);
+#else
                 mbar_arrive_expect_tx(b_full + st, bytes);
                 bulk_g2s(b_sm + st * b_bytes, p.packed + (ARR ? (size_t)it * NT * kpad : ((size_t)g * p.otiles + t) * NT * kpad), bytes, b_full + st);
+#endif
             }
         };
         stage_operands(0);
@@ -229,8 +257,18 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             const int st = j & 1;
             if (j + 1 < nitems) stage_operands(j + 1);          // overlaps the MMAs / epilogue of item j
             if (elect_one()) {
+#ifdef HSB_HEAD_PROF
+                const long long tw_ = clock64();
+#endif
                 mbar_wait(b_full + st, (j >> 1) & 1);
+#ifdef HSB_HEAD_PROF
+                prof_ld += clock64() - tw_;
+                const long long tw2_ = clock64();
+#endif
                 if (j >= 2) mbar_wait(d_empty + st, ((j >> 1) - 1) & 1);      // epilogue drained this accumulator
+#ifdef HSB_HEAD_PROF
+                prof_mma_wait += clock64() - tw2_;
+#endif
                 tc_fence_after_sync();
                 // arranged: the item's first channel (a multiple of 8 past the slab's first) selects the k-chunk of the resident slab
                 const int4 te = ARR ? (j < HD_TBL_ITEMS ? tbl_sm[j] : __ldg(p.table + it0 + j)) : make_int4(0, kpad, 0, 0);
@@ -266,7 +304,14 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             }
             const int nvalid = min(HC, max(o_end - o_base, 0) - half * HC);   // valid columns in this warp's half (may be <= 0)
             const int ncols = min(HC, (max(nvalid, 0) + 31) & ~31);
+#ifdef HSB_HEAD_PROF
+            const long long tw_ = clock64();
+#endif
             mbar_wait(d_full + st, (j >> 1) & 1);
+#ifdef HSB_HEAD_PROF
+            prof_wait += clock64() - tw_;
+            const long long tc_ = clock64();
+#endif
             tc_fence_after_sync();
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + st * NT + half * HC;
             for (int c = 0; c < ncols; c += 32) {
@@ -291,6 +336,10 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(d_empty + st);          // TMEM stage free again
+#ifdef HSB_HEAD_PROF
+            prof_ld += clock64() - tc_;
+            const long long tq_ = clock64();
+#endif
             // coalesced write-out of this warp's 32 rows x its column half: V columns per lane, 2 HC / (64 V)... rows per
             // instruction (16-byte lanes: 4 rows of 128 contiguous bytes each); V = the widest vector the start column allows
             if (nvalid > 0) {
@@ -306,8 +355,17 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
                 else head_copy_out<unsigned short, HC>(sbase, STAGE_PITCH, dbase, p.row_stride, nrows, nvalid, lane);
             }
             __syncwarp();       // staging rows are rewritten by the next item
+#ifdef HSB_HEAD_PROF
+            prof_copy += clock64() - tq_;
+#endif
         }
     }
+#ifdef HSB_HEAD_PROF
+    if (p.prof && (tid == 0 || tid == HD_EPI_WARPS * 32)) {
+        long long* o = p.prof + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 2 + (tid == 0 ? 0 : 1)) * 8;
+        o[0] = clock64() - prof_t0; o[1] = prof_pro; o[2] = prof_wait; o[3] = prof_ld; o[4] = prof_copy; o[5] = prof_mma_wait; o[6] = nitems;
+    }
+#endif
     tc_fence_before_sync();
     __syncthreads();
     if (warp == HD_EPI_WARPS) tmem_dealloc(tmem, 512);
@@ -403,7 +461,7 @@ extern "C" int hsb_signal2weights_packed_fwd(const void* s, const void* packed, 
     p.splits = splits;
     HSB_REQUIRE(splits <= 65535, HSB_ERR_UNSUPPORTED, "signal2weights_packed: grid too large");
     dim3 grid(tiles, splits);
-    p.table = nullptr; p.kpad_max = p.kpad; p.sig_end = 0;
+    p.table = nullptr; p.kpad_max = p.kpad; p.sig_end = 0; p.prof = nullptr;
     signal2weights_tc_kernel<HD_NT, false><<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
     note_kernel("signal2weights_tc_kernel");
     return check_launch("signal2weights_packed launch");
@@ -569,6 +627,27 @@ extern "C" int hsb_signal2weights_arranged_fwd(const void* s, const void* packed
     }
     p.splits = splits;
     dim3 grid(tiles, splits);
+    p.prof = nullptr;
+#ifdef HSB_HEAD_PROF
+    {
+        static long long* dprof = nullptr;
+        const int ctas = tiles * splits;
+        if (!dprof) cudaMalloc(&dprof, 4096 * 16 * sizeof(long long));
+        cudaMemsetAsync(dprof, 0, 4096 * 16 * sizeof(long long), (cudaStream_t)stream);
+        p.prof = dprof;
+        kern<<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
+        cudaStreamSynchronize((cudaStream_t)stream);
+        static long long host[4096 * 16];
+        cudaMemcpy(host, dprof, sizeof(long long) * ctas * 16, cudaMemcpyDeviceToHost);
+        double a[2][8] = {{0}};
+        for (int c = 0; c < ctas; ++c) for (int r = 0; r < 2; ++r) for (int k = 0; k < 8; ++k) a[r][k] += (double)host[(c * 2 + r) * 8 + k] / ctas;
+        fprintf(stderr, "[hsb-prof] head<arranged> grid %d x %d, %.1f items per CTA, smem %zu\n", tiles, splits, a[0][6], smem);
+        fprintf(stderr, "[hsb-prof]  epilogue warp 0: total %.0f cycles, prologue %.0f, wait d_full %.0f, TMEM->staging %.0f, copy out %.0f\n", a[0][0], a[0][1], a[0][2], a[0][3], a[0][4]);
+        fprintf(stderr, "[hsb-prof]  producer lane : total %.0f cycles, prologue %.0f, wait b_full %.0f, wait d_empty %.0f\n", a[1][0], a[1][1], a[1][3], a[1][5]);
+        note_kernel("signal2weights_tc_kernel<arranged>");
+        return check_launch("signal2weights_arranged launch");
+    }
+#endif
     kern<<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
     note_kernel("signal2weights_tc_kernel<arranged>");
     return check_launch("signal2weights_arranged launch");

@@ -3,6 +3,8 @@
     engine = SegmentationEngine(model, batch=8, height=512, width=1024)      # bf16, CUDA-graph captured
     labels = engine(frames)          # frames: pinned host float32 (B,3,H,W) -> pinned host uint8 (B,H,W)
 
+    engine = SegmentationEngine(model, 8, 512, 1024, input_dtype=torch.uint8)    # raw 8-bit frames, normalised on the device
+
 What it adds around the nn.Module mirror:
   * the stock-PyTorch parts (EfficientNet encoder, weight-mapper trunk) are put in inference form on a private
     copy of the model: eval-mode BatchNorms folded into the preceding convolutions, parameters cast to the
@@ -79,7 +81,14 @@ def fold_static_batchnorms(model: nn.Module, fused_epilogues: bool = True) -> in
 class SegmentationEngine:
     def __init__(self, model: nn.Module, batch: int, height: int, width: int, device="cuda",
                  dtype=torch.bfloat16, use_graph: bool = True, fold_bn: bool = True, warmup: int = 3,
-                 channels_last: bool = True):
+                 channels_last: bool = True, input_dtype=torch.float32,
+                 mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+        """``input_dtype=torch.float32``: frames arrive normalised, as the reference's transforms leave them
+        (hyperseg/test.py: ToTensor + Normalize on the host).  ``torch.uint8``: frames arrive as raw 0..255 RGB and
+        ``(x / 255 - mean) / std`` runs on the device in front of the encoder -- a quarter of the upload."""
+        if input_dtype not in (torch.float32, torch.uint8):
+            raise ValueError("input_dtype must be torch.float32 or torch.uint8")
+        self.input_dtype = input_dtype
         self.device = torch.device(device)
         self.dtype = dtype
         self.shape = (batch, 3, height, width)
@@ -108,7 +117,10 @@ class SegmentationEngine:
                 if isinstance(m, FoldedBatchNorm):
                     m.shift32 = m.shift_master.to(self.device, torch.float32).contiguous()
         self.stream = torch.cuda.Stream(self.device)
-        self.frames_dev = torch.zeros(self.shape, device=self.device, dtype=torch.float32)
+        self.frames_dev = torch.zeros(self.shape, device=self.device, dtype=input_dtype)
+        std_t = torch.tensor(std, dtype=torch.float32, device=self.device).view(1, 3, 1, 1)
+        self._in_scale = 1.0 / (255.0 * std_t)
+        self._in_bias = -torch.tensor(mean, dtype=torch.float32, device=self.device).view(1, 3, 1, 1) / std_t
         self.host_out = torch.empty((batch, height, width), dtype=torch.uint8).pin_memory()
         self.logits = None
         self.labels = None
@@ -132,13 +144,23 @@ class SegmentationEngine:
     def _forward_static(self):
         net = self.net
         # one pass: fp32 NCHW frames -> compute dtype, channels-last (the decoder's glue kernel takes any strides)
-        x = self.frames_dev.to(self.dtype, memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+        fmt = torch.channels_last if self.channels_last else torch.contiguous_format
+        if self.input_dtype == torch.uint8:       # normalise in fp32 (one rounding into the compute dtype, as on the host path)
+            x = torch.addcmul(self._in_bias, self.frames_dev.float(), self._in_scale).to(self.dtype, memory_format=fmt)
+        else:
+            x = self.frames_dev.to(self.dtype, memory_format=fmt)
         xin = x
         feats = net.backbone(xin)                  # NHWC feature maps are consumed as they are by the glue kernel
         signal = net.weight_mapper(feats[-1]).contiguous()      # NCHW once: every head reads position-contiguous rows
         self.logits = net.decoder.forward_features([x] + feats[:-1], signal)      # at the last decoder level's size
         # final bilinear upsample + argmax fused: full-resolution logits are never written
         self.labels = ops.upsample_argmax(self.logits, self.shape[-2:])
+
+    def _check_frames(self, frames):
+        if tuple(frames.shape) != self.shape:
+            raise ValueError(f"engine was built for frames of shape {self.shape}, got {tuple(frames.shape)}")
+        if frames.dtype != self.input_dtype:
+            raise ValueError(f"engine was built for {self.input_dtype} frames, got {frames.dtype}")
 
     @torch.no_grad()
     def step(self):
@@ -151,9 +173,8 @@ class SegmentationEngine:
 
     @torch.no_grad()
     def __call__(self, frames: torch.Tensor) -> torch.Tensor:
-        """Host frames (pinned float32, B x 3 x H x W) -> host labels (pinned uint8, B x H x W)."""
-        if tuple(frames.shape) != self.shape:
-            raise ValueError(f"engine was built for frames of shape {self.shape}, got {tuple(frames.shape)}")
+        """Host frames (pinned, ``input_dtype``, B x 3 x H x W) -> host labels (pinned uint8, B x H x W)."""
+        self._check_frames(frames)
         with torch.cuda.stream(self.stream):
             self.frames_dev.copy_(frames, non_blocking=True)
             if self.graph is not None:
@@ -169,7 +190,7 @@ class SegmentationEngine:
         if getattr(self, "_pipe", None) is None:
             self._pipe = dict(
                 copy_stream=torch.cuda.Stream(self.device),
-                staging=[torch.empty(self.shape, device=self.device, dtype=torch.float32) for _ in range(2)],
+                staging=[torch.empty(self.shape, device=self.device, dtype=self.input_dtype) for _ in range(2)],
                 host_out=[torch.empty(self.host_out.shape, dtype=torch.uint8).pin_memory() for _ in range(2)],
                 copied=[torch.cuda.Event() for _ in range(2)], consumed=[torch.cuda.Event() for _ in range(2)],
                 done=[torch.cuda.Event() for _ in range(2)], submitted=0, collected=0)
@@ -177,10 +198,9 @@ class SegmentationEngine:
 
     @torch.no_grad()
     def submit(self, frames: torch.Tensor) -> None:
-        """Enqueue one batch of host frames (pinned float32); at most two batches may be in flight.  The H2D copy runs
-        on its own stream into a staging buffer, so it overlaps the forward of the batch submitted before."""
-        if tuple(frames.shape) != self.shape:
-            raise ValueError(f"engine was built for frames of shape {self.shape}, got {tuple(frames.shape)}")
+        """Enqueue one batch of host frames (pinned, ``input_dtype``); at most two batches may be in flight.  The H2D copy
+        runs on its own stream into a staging buffer, so it overlaps the forward of the batch submitted before."""
+        self._check_frames(frames)
         p = self._pipeline()
         if p["submitted"] - p["collected"] >= 2:
             raise RuntimeError("two batches are already in flight: collect() one first")

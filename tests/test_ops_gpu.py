@@ -450,6 +450,31 @@ def test_engine_pipelined_stream_equals_blocking_calls():
     assert torch.equal(eng.collect(), want[0]) and torch.equal(eng.collect(), want[1])
 
 
+@pytest.mark.gpu
+def test_engine_uint8_frames_equal_host_normalised_frames():
+    """input_dtype=uint8: raw 8-bit frames normalised on the device give the label maps of the float32 path fed with the
+    same frames normalised on the host (the reference's ToTensor + Normalize); wrong dtypes are refused."""
+    from hyperseg_b200.engine import SegmentationEngine
+    from hyperseg_b200.synthetic import build_model
+    model = build_model("hyperseg-m", seed=0).eval()
+    g = torch.Generator().manual_seed(77)
+    u8 = torch.randint(0, 256, (2, 3, 128, 256), generator=g, dtype=torch.uint8).pin_memory()
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    f32 = ((u8.float() / 255 - mean) / std).pin_memory()
+    e8 = SegmentationEngine(model, 2, 128, 256, input_dtype=torch.uint8)
+    ef = SegmentationEngine(model, 2, 128, 256)
+    a, b = e8(u8).clone(), ef(f32).clone()
+    la, lb = e8.full_logits().float(), ef.full_logits().float()
+    # same network input up to one bf16 rounding of (x * scale + bias) vs ((x / 255 - mean) / std)
+    assert rel_err(la.cpu(), lb.cpu()) < 2e-2
+    assert (a == b).float().mean().item() > 0.99
+    with pytest.raises(ValueError):
+        e8(f32)
+    with pytest.raises(ValueError):
+        ef.submit(u8)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # restage-free tensor-core MetaBlock kernel (hsb_patch_ir_arranged_fwd) and the arranged weight head
 # ---------------------------------------------------------------------------------------------------------
