@@ -247,6 +247,9 @@ static int dispatch_1x1(Conv1x1Params& p, cudaStream_t st) {
     return launch_1x1<T, 1, 1>(p, smem, st);
 }
 
+int conv1x1_ring_try(const void* x, const void* w, void* y, const float* post_scale, const float* post_shift, int act, int B, int Cin,
+                     int Cout, int H, int W, int fh, int fw, int groups, int64_t w_row_stride, cudaStream_t st, bool* handled);
+
 }  // namespace hsb
 
 using namespace hsb;
@@ -283,6 +286,11 @@ extern "C" int hsb_patch_conv1x1_fwd(const void* x, const void* w, void* y,
                 ((size_t)p.hp * es) % 16 == 0 && ((size_t)w_row_stride * es) % 16 == 0;
     HSB_REQUIRE((int64_t)B * fh * fw < (1ll << 31), HSB_ERR_UNSUPPORTED, "patch_conv1x1: too many patches");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == HSB_BF16 && w_layout == HSB_W_PATCH_MAJOR) {       // the decoder's case: persistent ring kernel when it fits
+        bool handled = false;
+        const int rc = conv1x1_ring_try(x, w, y, post_scale, post_shift, act, B, Cin, Cout, H, W, fh, fw, groups, w_row_stride, st, &handled);
+        if (handled) return rc;
+    }
     if (dtype == HSB_F32) return dispatch_1x1<float>(p, st);
     return dispatch_1x1<__nv_bfloat16>(p, st);
 }

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             kg_lo = max(0, (lo - sig_first) >> 3); kg_hi = min(kg_hi, (hi - sig_first + 7) >> 3);
         }
         const int chunk0 = kg_lo * HD_M, chunks = kg_hi * HD_M;       // 128 chunks (16 units x 8 channels) per group
-        constexpr int DEPTH = 10;                  // 16-byte loads in flight per thread
+        constexpr int DEPTH = 14;                  // 16-byte loads in flight per thread: one round for a 240-channel range
         for (int base = chunk0; base < chunks; base += DEPTH * HD_THREADS) {
             uint4 v[DEPTH];
 #pragma unroll

@@ -29,6 +29,9 @@ elif which in ("ir2", "ir2_3"):
 elif which == "conv0":
     x = rnd(B, 82, 16, 32); wt = ops.weights_to_patch_major(rnd(B, 82 * 64, 16, 32, scale=0.3)); sc, sh = bn(64)
     fn = lambda: ops.patch_conv1x1(x, wt, 64, 1, sc, sh, "relu")
+elif which == "conv1":
+    x = rnd(B, 94, 32, 64); wt = ops.weights_to_patch_major(rnd(B, 94 * 32, 16, 32, scale=0.3)); sc, sh = bn(32)
+    fn = lambda: ops.patch_conv1x1(x, wt, 32, 1, sc, sh, "relu")
 elif which == "conv2":
     x = rnd(B, 44, 64, 128); wt = ops.weights_to_patch_major(rnd(B, 44 * 16, 16, 32, scale=0.3)); sc, sh = bn(16)
     fn = lambda: ops.patch_conv1x1(x, wt, 16, 1, sc, sh, "relu")

@@ -3,11 +3,16 @@ profiles/<round>_ncu_full_summary.txt and profiles/<round>_traffic.json.   pytho
 import csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TAGS = [("ir", "hsb_patch_ir_fwd, tcgen05 path, HyperSeg-M level 4 (B=8, 34->68->19, 256x512, 16x16 patches, bf16)"),
+TAGS = [("ir2", "hsb_patch_ir_arranged_fwd (patch_ir2_kernel), HyperSeg-M level 4 (B=8, 34->68->19, 256x512, 16x16 patches, bf16)"),
+        ("ir2_3", "hsb_patch_ir_arranged_fwd (patch_ir2_kernel), level 3 (B=8, 24->48->16, 128x256, 8x8 patches)"),
+        ("head4a", "hsb_signal2weights_arranged_fwd, level-4 head writing arranged rows (320 -> 4704-element rows, groups 4, B=8)"),
+        ("head3a", "hsb_signal2weights_arranged_fwd, level-3 head writing arranged rows (192 -> 2352, groups 16)"),
+        ("ir", "hsb_patch_ir_fwd, reference-order tcgen05 path (round 1), HyperSeg-M level 4 (B=8, 34->68->19, 256x512, 16x16 patches, bf16)"),
         ("ir3", "hsb_patch_ir_fwd, tcgen05 path, level 3 (B=8, 24->48->16, 128x256, 8x8 patches)"),
         ("head4", "hsb_signal2weights_packed_fwd, level-4 head (320 -> 4216, groups 4, B=8)"),
         ("head0", "hsb_signal2weights_packed_fwd, level-0 head (416 -> 5248, groups 32)"),
-        ("conv0", "hsb_patch_conv1x1_fwd, level 0 (82 -> 64, 1x1 patches)"),
+        ("conv0", "hsb_patch_conv1x1_fwd, level 0 (82 -> 64, 1x1 patches; round 2: conv1x1_ring_kernel)"),
+        ("conv1", "hsb_patch_conv1x1_fwd, level 1 (94 -> 32, 2x2 patches)"),
         ("conv2", "hsb_patch_conv1x1_fwd, level 2 (44 -> 16, 4x4 patches)"),
         ("epi", "hsb_bias_act_nhwc_fwd, encoder epilogue (shift + swish + SE partial sums), B=8, 96 ch, 256x512, bf16")]
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -44,6 +49,8 @@ def main(rnd):
                     b = float(vals[col[m]].replace(",", "")) * TO_BYTES.get(units[col[m]], 1.0)
                     rd, wr = (b, wr) if "read" in m else (rd, b)
         traffic[tag] = rd + wr
+        if tag == "ir2":
+            traffic["ir2_l4"] = rd + wr          # the key bench.py reads for roofline.traffic
         out.append("")
     hdr = (f"ncu --set full --clock-control none --import-source on, one launch each at the HyperSeg-M batch-8 shape "
            f"(scripts/run_kernel.py, scripts/gpu_final.sh, summarised by scripts/summarize_ncu.py); B200, round {rnd[1:]}.\n"

@@ -585,6 +585,28 @@ def test_kernel_selection_is_observable():
     assert _lib.last_kernel() == "signal2weights_kernel"
 
 
+@pytest.mark.parametrize("geom", [(82, 64, 16, 32, 2), (130, 32, 24, 48, 1), (82, 64, 18, 24, 3), (20, 6, 5, 16, 2)])
+def test_conv1x1_ring_kernel_one_pixel_patches(geom):
+    """The persistent ring kernel (bf16, patch-major rows, one pixel per patch: the coarsest decoder level of every shipped
+    configuration) against the float64 oracle, with and without the fused BatchNorm + ReLU; patch counts that do not divide by
+    the SM count, a patch grid whose width is not a power of two, and the general kernel on the same data as a cross-check."""
+    from hyperseg_b200 import _lib
+    Cin, Cout, fh, fw, B = geom
+    x = _rand((B, Cin, fh, fw), 90).to(DEV, torch.bfloat16)
+    w = _rand((B, Cin * Cout, fh, fw), 91, 0.3).to(DEV, torch.bfloat16)
+    scale, shift = _bn(Cout, 92)
+    wl = ops.weights_to_patch_major(w)
+    for fused in (True, False):
+        args = (scale.to(DEV), shift.to(DEV), "relu") if fused else (None, None, "none")
+        ref = orc.patch_conv1x1(x.float().cpu(), w.float().cpu(), Cout, 1, *((scale, shift, "relu") if fused else (None, None, "none")))
+        y = ops.patch_conv1x1(x, wl, Cout, 1, *args)
+        assert _lib.last_kernel() == "conv1x1_ring_kernel", _lib.last_kernel()
+        assert rel_err(y.float().cpu(), ref) < BF16_TOL
+        y_general = ops.patch_conv1x1(x, w, Cout, 1, *args)                 # reference-layout weights: the one-shot kernel
+        assert _lib.last_kernel() == "patch_conv1x1_kernel"
+        assert rel_err(y.float().cpu(), y_general.float().cpu()) < 1e-2
+
+
 def test_ir_module_takes_the_arranged_fast_path_in_bf16():
     """HyperPatchInvertedResidual (own head) under autocast: head -> arranged rows -> restage-free kernel, and the result
     agrees with the module's fp32 path (CUDA-core kernels)."""
