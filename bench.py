@@ -308,7 +308,8 @@ def kernel_rooflines(bc, batch: int, with_gpu_reference: bool):
             fns.append(lambda x=x, wt=wt, sc=sc, sh=sh, cout=cout: ops.patch_conv1x1(x, wt, cout, 1, sc, sh, "relu"))
             keep = (x, wt, sc, sh)
         ms = time_graph(fns)
-        out[f"L{li}_conv1x1"] = {"ms": ms, "bytes": es * (cin * h * w + cin * cout * P + cout * h * w) * batch}
+        from hyperseg_b200 import _lib as _l
+        out[f"L{li}_conv1x1"] = {"ms": ms, "bytes": es * (cin * h * w + cin * cout * P + cout * h * w) * batch, "kernel": _l.last_kernel()}
         if with_gpu_reference:
             x, wt, sc, sh = keep
             b = tgb.make_bn(cout, sc, sh, dev)
@@ -347,7 +348,8 @@ def kernel_rooflines(bc, batch: int, with_gpu_reference: bool):
             fns.append(lambda s=s, ws=ws, sc_=sc_, hp=hp, groups=groups: ops.signal2weights(s, ws, 0, sc_, hp, groups))
             keep = (s, ws)
         nbytes = es * (sc_ * P * batch + hp * sc_ // groups + hp * P * batch)
-        out[f"L{li}_head"] = {"ms": time_graph(fns), "bytes": nbytes, "kernel": "signal2weights_tc_kernel (reference-order rows)"}
+        from hyperseg_b200 import _lib as _l
+        out[f"L{li}_head"] = {"ms": time_graph(fns), "bytes": nbytes, "kernel": _l.last_kernel() + " (reference-order rows)"}
         # the arranged variant feeds the inverted-residual levels (a shared unify head feeds several: one pack per level)
         feeds = [lv for lv in ir_levels if lv == li] if len(bc["heads"]) == nconv + len(bc["ir"]) else (list(ir_levels) if li == len(bc["heads"]) - 1 else [])
         off = 0

@@ -46,6 +46,7 @@ struct HeadTCParams {
     const int4* table;                // arranged mode: per item {first signal channel, kpad, first output column, columns};
                                       // the packed tile of item i starts at element i * nt * kpad_max
     int kpad_max, sig_end;            // arranged mode: operand stages are sized for kpad_max; signal channels >= sig_end read as 0
+    int sig_first, tbl_base;          // first channel of the resident slab; added to the table's first-channel entries
     int64_t ssb, ssc;                 // signal strides (elements); position stride is 1
     int64_t row_stride;               // output row stride (elements)
     long long* prof;                  // profiling build (-DHSB_HEAD_PROF): 8 counters per CTA
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
     const int it0 = blockIdx.y * per, it1 = min(p.items, it0 + per);
     const int nitems = it1 - it0;
     if (nitems <= 0) return;
+    auto item = [&](int j) { if (j < HD_TBL_ITEMS) return tbl_sm[j]; int4 e = __ldg(p.table + it0 + j); e.x += p.tbl_base; return e; };
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -147,12 +149,12 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
         // the head's whole signal slice for these 128 positions, MN-major: unit(mc, k) = (k/8)*LBO + mc*128 + (k%8)*16 holds
         // 8 consecutive positions of channel sig_first + k (sig_first = slice start rounded down to 8); channels outside
         // the slice are zero (their packed weights are zero as well)
-        const int sig_first = p.sig_index & ~7;
+        const int sig_first = p.sig_first;
         if (tid < HD_M / 8) {
             const int n = n0 + tid * 8;                                   // P % 8 == 0: a unit never straddles images
             pos_sm[tid] = n < p.NTOT ? (int64_t)(n / p.P) * p.ssb + n % p.P : -1;
         }
-        for (int j = tid; j < min(nitems, HD_TBL_ITEMS); j += HD_THREADS) tbl_sm[j] = __ldg(p.table + it0 + j);
+        for (int j = tid; j < min(nitems, HD_TBL_ITEMS); j += HD_THREADS) { int4 e = __ldg(p.table + it0 + j); e.x += p.tbl_base; tbl_sm[j] = e; }
         __syncthreads();
         // the packed weights of the first two items do not depend on the slab: their copies fly while it is staged
         if (tid == HD_EPI_WARPS * 32) {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             const int st = j & 1, it = it0 + j;
             int g, t, k_first, k_count, k_item;      // slab id, tile, first signal channel, channels to copy, item's padded K
             if (ARR) {
-                const int4 e = j < HD_TBL_ITEMS ? tbl_sm[j] : __ldg(p.table + it);
+                const int4 e = item(j);
                 g = e.x * 4096 + e.y; t = 0; k_first = e.x; k_item = e.y; k_count = max(0, min(e.y, p.sig_end - e.x));
             } else {
                 g = it / p.otiles; t = it % p.otiles; k_first = p.sig_index + g * p.spg; k_count = p.spg; k_item = kpad;
@@ -271,8 +273,8 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
 #endif
                 tc_fence_after_sync();
                 // arranged: the item's first channel (a multiple of 8 past the slab's first) selects the k-chunk of the resident slab
-                const int4 te = ARR ? (j < HD_TBL_ITEMS ? tbl_sm[j] : __ldg(p.table + it0 + j)) : make_int4(0, kpad, 0, 0);
-                const uint32_t a_addr = ARR ? smem_u32(a_sm) + ((te.x - (p.sig_index & ~7)) >> 3) * a_lbo : smem_u32(a_sm + st * a_bytes);
+                const int4 te = ARR ? item(j) : make_int4(0, kpad, 0, 0);
+                const uint32_t a_addr = ARR ? smem_u32(a_sm) + ((te.x - p.sig_first) >> 3) * a_lbo : smem_u32(a_sm + st * a_bytes);
                 const uint32_t b_addr = smem_u32(b_sm + st * b_bytes);
                 const int ksteps = te.y / 16;
                 for (int s = 0; s < ksteps; ++s) {
@@ -295,8 +297,8 @@ __global__ void __launch_bounds__(HD_THREADS, 1) signal2weights_tc_kernel(const 
             const int st = j & 1, it = it0 + j;
             int o_base, o_end;
             if (ARR) {
-                const int4 e = j < HD_TBL_ITEMS ? tbl_sm[j] : __ldg(p.table + it);
-                o_base = e.z; o_end = e.z + e.w;
+                const int4 e = item(j);
+                o_base = e.z; o_end = min(e.z + e.w, p.hp);
             } else {
                 const int g = it / p.otiles, t = it % p.otiles;
                 o_base = g * p.opg + t * NT;
@@ -395,12 +397,90 @@ __global__ void head_pack_kernel(const T* __restrict__ ws, __nv_bfloat16* __rest
     }
 }
 
+// ---- reference-order rows with the signal slice resident (same kernel mode as the arranged rows) -----------------------------
+// The K = 12..80 heads spent their time re-staging a 4 KB signal slab per (group, tile) item.  Keeping the head's whole signal
+// slice in shared memory (as the arranged heads do) turns an item into "stream one packed weight tile, issue 1-3 MMAs":
+// items are 128-column tiles of the reference-order row that may straddle groups (K = union of their signal ranges, zero
+// blocks in the packed weights), planned greedily in 8-column units.  The packed buffer carries its own item table:
+//   [int4 table[items]] [pad to 128 B] [items x 128 x kpad_max bf16]
+constexpr int HD_NT_RO = 128;
+
+struct ResidentPlan {
+    int items, kpad_max, sig_pad;
+    std::vector<int4> table;               // {first signal channel relative to sig_index (multiple of 8), kpad, first column, columns}
+};
+
+static bool plan_resident(int sig_ch, int out_ch, int groups, ResidentPlan* pl) {
+    if (sig_ch <= 0 || out_ch <= 0 || groups <= 0 || sig_ch % groups || out_ch % groups) return false;
+    const int spg = sig_ch / groups, opg = out_ch / groups;
+    pl->sig_pad = (sig_ch + 15) / 16 * 16 + 16;
+    pl->kpad_max = 16;
+    pl->table.clear();
+    const long budget = 227L * 1024 - (long)pl->sig_pad * HD_M * 2 - (long)HD_M * (HD_NT_RO * 2 + 16) - 2048 - HD_TBL_BYTES;
+    const int KLIM = (int)std::min<long>(160, budget / (2 * HD_NT_RO * 2) / 16 * 16);     // 160: a tile straddling two 80-channel groups
+    if (KLIM < 16) return false;
+    auto kfirst_of = [&](int lo) { return (lo * spg) & ~7; };
+    auto kpad_of = [&](int lo, int hi) { return ((hi + 1) * spg - kfirst_of(lo) + 15) / 16 * 16; };
+    int c0 = 0, gmin = groups, gmax = -1;
+    auto flush = [&](int c1) {
+        pl->table.push_back(make_int4(kfirst_of(gmin), kpad_of(gmin, gmax), c0, c1 - c0));
+        pl->kpad_max = std::max(pl->kpad_max, kpad_of(gmin, gmax));
+        c0 = c1; gmin = groups; gmax = -1;
+    };
+    for (int u = 0; u < out_ch; u += 8) {
+        const int ulo = u / opg, uhi = (std::min(u + 8, out_ch) - 1) / opg;
+        if (kpad_of(ulo, uhi) > KLIM) return false;              // one unit alone is too wide
+        const int nlo = std::min(gmin, ulo), nhi = std::max(gmax, uhi);
+        if (u > c0 && (u - c0 >= HD_NT_RO || kpad_of(nlo, nhi) > KLIM)) flush(u);
+        gmin = std::min(gmin, ulo); gmax = std::max(gmax, uhi);
+    }
+    flush(out_ch);
+    pl->items = (int)pl->table.size();
+    return head_smem_bytes_arranged(pl->sig_pad, pl->kpad_max, HD_NT_RO) <= 227 * 1024;
+}
+
+static inline size_t resident_table_bytes(int items) { return ((size_t)items * sizeof(int4) + 127) / 128 * 128; }
+
+// legacy layout (one A slab per item) only where the slice does not fit one CTA; HSB_HEAD_LEGACY=1 forces it (A/B timing)
+static bool use_resident(int sig_ch, int out_ch, int groups, ResidentPlan* pl) {
+    static const bool legacy = [] { const char* v = getenv("HSB_HEAD_LEGACY"); return v && v[0] == '1'; }();
+    return !legacy && plan_resident(sig_ch, out_ch, groups, pl);
+}
+
+template <typename T>
+__global__ void head_pack_resident_kernel(const T* __restrict__ ws, __nv_bfloat16* __restrict__ out, const int4* __restrict__ table,
+                                          const float* __restrict__ scale, int spg, int opg, int out_ch, int items, int kpad_max) {
+    const size_t per_item = (size_t)HD_NT_RO * kpad_max;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < per_item * items; i += (size_t)gridDim.x * blockDim.x) {
+        const int it = (int)(i / per_item);
+        size_t r = i % per_item;
+        const int4 e = table[it];
+        float v = 0.f;
+        if (r < (size_t)HD_NT_RO * e.y) {
+            const int k8 = r % 8; r /= 8;
+            const int n8 = r % 8; r /= 8;
+            const int nc = r % (HD_NT_RO / 8); r /= (HD_NT_RO / 8);
+            const int kc = (int)r, col = e.z + nc * 8 + n8;
+            if (nc * 8 + n8 < e.w && col < out_ch) {
+                const int k = e.x + kc * 8 + k8 - (col / opg) * spg;          // channel inside the group of this output
+                if (k >= 0 && k < spg) {
+                    v = ld_f(ws + (size_t)col * spg + k);
+                    if (scale) v *= scale[col];
+                }
+            }
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
 }  // namespace hsb
 
 using namespace hsb;
 
 extern "C" int64_t hsb_head_packed_elems(int sig_ch, int out_ch, int groups) {
     if (sig_ch <= 0 || out_ch <= 0 || groups <= 0 || sig_ch % groups || out_ch % groups) return -1;
+    ResidentPlan pl;
+    if (use_resident(sig_ch, out_ch, groups, &pl)) return (int64_t)(resident_table_bytes(pl.items) / 2) + (int64_t)pl.items * HD_NT_RO * pl.kpad_max;
     const int spg = sig_ch / groups, opg = out_ch / groups;
     const int kpad = (spg + 15) / 16 * 16, otiles = ceil_div(opg, HD_NT);
     return (int64_t)groups * otiles * HD_NT * kpad;
@@ -415,6 +495,21 @@ extern "C" int hsb_head_pack(const void* ws, void* packed, const float* row_scal
     const int kpad = (spg + 15) / 16 * 16, otiles = ceil_div(opg, HD_NT);
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = std::max(1, device_sm_count()) * 4;
+    ResidentPlan pl;
+    if (use_resident(sig_ch, out_ch, groups, &pl)) {
+        HSB_REQUIRE(((uintptr_t)packed % 16) == 0, HSB_ERR_UNSUPPORTED, "head_pack: packed buffer must be 16-byte aligned");
+        // one-time operation: the table is tiny, a synchronous copy keeps the host vector's lifetime simple
+        cudaError_t ce = cudaMemcpyAsync(packed, pl.table.data(), pl.table.size() * sizeof(int4), cudaMemcpyHostToDevice, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("head_pack: table copy: ") + cudaGetErrorString(ce));
+        __nv_bfloat16* tiles = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(packed) + resident_table_bytes(pl.items));
+        if (dtype == HSB_F32)
+            head_pack_resident_kernel<float><<<blocks, 256, 0, st>>>((const float*)ws, tiles, (const int4*)packed, row_scale, spg, opg, out_ch, pl.items, pl.kpad_max);
+        else
+            head_pack_resident_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)ws, tiles, (const int4*)packed, row_scale, spg, opg, out_ch,
+                                                                             pl.items, pl.kpad_max);
+        return check_launch("head_pack (resident) launch");
+    }
     if (dtype == HSB_F32)
         head_pack_kernel<float><<<blocks, 256, 0, st>>>((const float*)ws, (__nv_bfloat16*)packed, row_scale, out_ch, spg,
                                                         kpad, opg, groups, otiles);
@@ -439,6 +534,33 @@ extern "C" int hsb_signal2weights_packed_fwd(const void* s, const void* packed, 
     HSB_REQUIRE(((uintptr_t)s % 16) == 0 && (s_stride_b % 8) == 0 && (s_stride_c % 8) == 0 && ((uintptr_t)packed % 16) == 0,
                 HSB_ERR_UNSUPPORTED, "signal2weights_packed: signal / packed weights must be 16-byte aligned");
     HeadTCParams p;
+    ResidentPlan pl;
+    if (use_resident(sig_ch, out_ch, groups, &pl)) {
+        int n_items = 0;                                     // items that start before hp (the kernel clips the last one)
+        while (n_items < pl.items && pl.table[n_items].z < hp) ++n_items;
+        p.s = (const __nv_bfloat16*)s; p.out = (__nv_bfloat16*)w_out;
+        p.table = (const int4*)packed;
+        p.packed = reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const unsigned char*>(packed) + resident_table_bytes(pl.items));
+        p.NTOT = B * P; p.P = P; p.sig_index = sig_index; p.spg = 0; p.kpad = pl.sig_pad; p.opg = 0; p.hp = hp; p.groups = 1; p.otiles = n_items;
+        p.ssb = s_stride_b; p.ssc = s_stride_c; p.row_stride = out_row_stride;
+        p.kpad_max = pl.kpad_max; p.sig_end = sig_index + sig_ch; p.sig_first = sig_index; p.tbl_base = sig_index; p.prof = nullptr;
+        const size_t smem = head_smem_bytes_arranged(pl.sig_pad, pl.kpad_max, HD_NT_RO);
+        auto kern = signal2weights_tc_kernel<HD_NT_RO, true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("signal2weights_packed attr: ") + cudaGetErrorString(e));
+        p.items = n_items;
+        const int tiles = ceil_div(p.NTOT, HD_M), sms = std::max(1, device_sm_count());
+        int splits = 1, best = ceil_div(tiles, sms) * (p.items + 4);
+        for (int sp = 2; sp <= p.items; ++sp) {
+            const int cost = ceil_div(tiles * sp, sms) * (ceil_div(p.items, sp) + 4);
+            if (cost < best) { best = cost; splits = sp; }
+        }
+        p.splits = splits;
+        HSB_REQUIRE(splits <= 65535, HSB_ERR_UNSUPPORTED, "signal2weights_packed: grid too large");
+        kern<<<dim3(tiles, splits), HD_THREADS, smem, (cudaStream_t)stream>>>(p);
+        note_kernel("signal2weights_tc_kernel<resident>");
+        return check_launch("signal2weights_packed launch");
+    }
     p.s = (const __nv_bfloat16*)s; p.packed = (const __nv_bfloat16*)packed; p.out = (__nv_bfloat16*)w_out;
     p.NTOT = B * P; p.P = P; p.sig_index = sig_index; p.spg = sig_ch / groups; p.kpad = (p.spg + 15) / 16 * 16;
     p.opg = out_ch / groups; p.hp = hp; p.groups = groups; p.otiles = ceil_div(p.opg, HD_NT);
@@ -461,7 +583,7 @@ extern "C" int hsb_signal2weights_packed_fwd(const void* s, const void* packed, 
     p.splits = splits;
     HSB_REQUIRE(splits <= 65535, HSB_ERR_UNSUPPORTED, "signal2weights_packed: grid too large");
     dim3 grid(tiles, splits);
-    p.table = nullptr; p.kpad_max = p.kpad; p.sig_end = 0; p.prof = nullptr;
+    p.table = nullptr; p.kpad_max = p.kpad; p.sig_end = 0; p.prof = nullptr; p.sig_first = 0; p.tbl_base = 0;
     signal2weights_tc_kernel<HD_NT, false><<<grid, HD_THREADS, smem, (cudaStream_t)stream>>>(p);
     note_kernel("signal2weights_tc_kernel");
     return check_launch("signal2weights_packed launch");
@@ -611,7 +733,7 @@ extern "C" int hsb_signal2weights_arranged_fwd(const void* s, const void* packed
     const int sig_pad = ((sig_index & 7) + sig_ch + 15) / 16 * 16 + 16;
     p.NTOT = B * P; p.P = P; p.sig_index = sig_index; p.spg = 0; p.kpad = sig_pad; p.opg = 0; p.hp = row_elems; p.groups = 1; p.otiles = n_items;
     p.ssb = s_stride_b; p.ssc = s_stride_c; p.row_stride = out_row_stride;
-    p.table = (const int4*)table; p.kpad_max = kpad_max; p.sig_end = sig_index + sig_ch;
+    p.table = (const int4*)table; p.kpad_max = kpad_max; p.sig_end = sig_index + sig_ch; p.sig_first = sig_index & ~7; p.tbl_base = 0;
     const size_t smem = head_smem_bytes_arranged(sig_pad, kpad_max, HD_NT_ARR);
     HSB_REQUIRE(smem <= 227 * 1024, HSB_ERR_UNSUPPORTED, "signal2weights_arranged: the signal slice does not fit one CTA");
     auto kern = signal2weights_tc_kernel<HD_NT_ARR, true>;
