@@ -468,8 +468,9 @@ def run_ours(args):
     # ---- e2e: host frames in, host labels out ----
     # submit()/collect(): every step uploads its own frames from pinned host memory and reads its own label map back;
     # the upload of step k+1 overlaps the forward of step k (two batches in flight)
-    for i in range(min(3, args.warmup)):
-        engine(host_frames[i % rotate])
+    for i in range(max(3, min(5, args.warmup))):     # warm-up through the same calls (creates the staging / pinned buffers)
+        engine.submit(host_frames[i % rotate])
+        engine.collect()
     barrier()
     e2e_start = time.perf_counter()
     checksum = 0
@@ -487,8 +488,9 @@ def run_ours(args):
     mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
     std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
     host_u8 = [((f * std + mean) * 255).round().clamp(0, 255).to(torch.uint8).pin_memory() for f in host_frames]
-    for i in range(min(3, args.warmup)):
-        engine8(host_u8[i % rotate])
+    for i in range(max(3, min(5, args.warmup))):
+        engine8.submit(host_u8[i % rotate])
+        engine8.collect()
     barrier()
     u8_start = time.perf_counter()
     for i in range(args.steps):
