@@ -149,6 +149,179 @@ __global__ void __launch_bounds__(RING_MAX_THREADS, 1) conv1x1_ring_kernel(const
     }
 }
 
+// ---- the same ring, arithmetic on the tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32) -------------------------------
+// One warp owns one patch of the unit at a time: D[Cout x pixels] = W[Cout x Cin] . X[Cin x pixels].  The weight row is read
+// from shared memory exactly once, as A fragments (32-bit loads of channel pairs: no unpacking, no FMA instructions -- a
+// one-pixel patch needs ~160 warp instructions instead of ~500); X comes as B fragments (the patch's pixels are the N
+// columns: 8 per tile, zero-filled past the patch).  MT = Cout tiles of 16, NTP = pixel tiles of 8 per patch.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int MMA_CONSUMERS = 8, MMA_THREADS = 32 * (MMA_CONSUMERS + 1), MMA_MAX_SLOTS = 16, MMA_MAX_STAGES = 4;
+constexpr int MMA_BAR_BYTES = 2048;       // full_w / empty_w [stage][slot], full_x / empty_x [stage]
+
+template <int MT, int NTP>
+__global__ void __launch_bounds__(MMA_THREADS, 1) conv1x1_mma_kernel(const __grid_constant__ CUtensorMap xmap, const RingParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // The ring is refilled per PATCH SLOT, not per unit: a warp releases the weight row of its patch as soon as it has
+    // consumed it and the producer warp streams the row of the unit S steps ahead into that slot at once, so the S x PG rows
+    // of the ring are in flight all the time (with whole-unit stages only one 84 KB copy was in flight after the first two).
+    uint64_t* full_w = reinterpret_cast<uint64_t*>(smem);                       // [S][MMA_MAX_SLOTS]
+    uint64_t* empty_w = full_w + MMA_MAX_STAGES * MMA_MAX_SLOTS;                // [S][MMA_MAX_SLOTS]
+    uint64_t* full_x = empty_w + MMA_MAX_STAGES * MMA_MAX_SLOTS;                // [S]
+    uint64_t* empty_x = full_x + MMA_MAX_STAGES;                                // [S]
+    unsigned char* stage0 = smem + MMA_BAR_BYTES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;                    // fragment coordinates: group id, thread in group
+    const int S = p.stages;
+    const int u0 = (int)((long long)blockIdx.x * p.units / gridDim.x), u1 = (int)((long long)(blockIdx.x + 1) * p.units / gridDim.x);
+    const int n = u1 - u0;
+    const int users = min(MMA_CONSUMERS, p.PG);               // warps that own at least one slot: they release the x tile
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            for (int q = 0; q < p.PG; ++q) { mbar_init(full_w + s * MMA_MAX_SLOTS + q, 1); mbar_init(empty_w + s * MMA_MAX_SLOTS + q, 1); }
+            mbar_init(full_x + s, 1);
+            mbar_init(empty_x + s, users);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&xmap);
+    }
+    __syncthreads();
+    const int PGW = p.PG * p.pw, plane = p.ph * PGW, npix = p.ph * p.pw;
+    const uint32_t w_bytes = (uint32_t)p.hp * 2, x_bytes = (uint32_t)(p.Cin * plane * 2);
+
+    if (warp == MMA_CONSUMERS) {
+        // ================= producer warp (one lane) =================
+        if (lane == 0) {
+            for (int k = 0; k < n; ++k) {
+                const int u = u0 + k, s = k % S;
+                const uint32_t par = ((k / S) & 1) ^ 1;               // the slot's previous user (unit k - S) has released it
+                const int jg = u % p.upr, bi = u / p.upr, b = bi / p.fh, pi = bi % p.fh;
+                unsigned char* st = stage0 + (size_t)s * p.stage_bytes;
+                if (k >= S) mbar_wait(empty_x + s, par);
+                mbar_arrive_expect_tx(full_x + s, x_bytes);
+                tma_load_4d(st + p.x_off, &xmap, jg * PGW, pi * p.ph, 0, b, full_x + s);
+                const __nv_bfloat16* wsrc = p.w + ((size_t)bi * p.fw + (size_t)jg * p.PG) * p.w_row_stride;
+                for (int q = 0; q < p.PG; ++q) {
+                    if (k >= S) mbar_wait(empty_w + s * MMA_MAX_SLOTS + q, par);
+                    mbar_arrive_expect_tx(full_w + s * MMA_MAX_SLOTS + q, w_bytes);
+                    bulk_g2s(st + (size_t)q * p.wrow * 2, wsrc + (size_t)q * p.w_row_stride, w_bytes, full_w + s * MMA_MAX_SLOTS + q);
+                }
+            }
+        }
+        return;
+    }
+
+    // per lane: offsets of its B-fragment pixels inside the x tile (column n = g of every pixel tile), -1 past the patch
+    int xoff[NTP];
+#pragma unroll
+    for (int j = 0; j < NTP; ++j) {
+        const int pp = j * 8 + g;
+        xoff[j] = pp < npix ? (pp / p.pw) * PGW + pp % p.pw : -1;
+    }
+    // epilogue constants of the lane's output channels (rows g and g + 8 of every Cout tile)
+    float sc[MT][2], sh[MT][2];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int oc = m * 16 + h * 8 + g;
+            sc[m][h] = (p.post_scale && oc < p.Cout) ? __ldg(p.post_scale + oc) : 1.f;
+            sh[m][h] = (p.post_scale && oc < p.Cout) ? __ldg(p.post_shift + oc) : 0.f;
+        }
+    const int ksteps = (p.Cin + 15) / 16;
+    const size_t ostride = (size_t)p.H * p.W;
+    for (int k = 0; k < n; ++k) {
+        const int s = k % S, u = u0 + k;
+        const uint32_t par = (k / S) & 1;
+        const int jg = u % p.upr, bi = u / p.upr, b = bi / p.fh, pi = bi % p.fh;
+        const unsigned char* st = stage0 + (size_t)s * p.stage_bytes;
+        const unsigned short* xs = reinterpret_cast<const unsigned short*>(st + p.x_off);
+        if (warp < users) mbar_wait(full_x + s, par);
+        for (int q = warp; q < p.PG; q += MMA_CONSUMERS) {
+            mbar_wait(full_w + s * MMA_MAX_SLOTS + q, par);
+            const __nv_bfloat16* wq = reinterpret_cast<const __nv_bfloat16*>(st) + (size_t)q * p.wrow;
+            const unsigned short* xq = xs + q * p.pw;
+            float acc[MT][NTP][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int j = 0; j < NTP; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+#pragma unroll 2
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const int k0 = ks * 16 + 2 * t;                               // this lane's channel pairs: k0, k0 + 8
+                const bool v0 = k0 < p.Cin, v1 = k0 + 8 < p.Cin;              // Cin is even: a pair is valid or not as a whole
+                uint32_t bf[NTP][2];
+#pragma unroll
+                for (int j = 0; j < NTP; ++j) {
+                    bf[j][0] = bf[j][1] = 0u;
+                    if (xoff[j] >= 0) {
+                        const unsigned short* xp = xq + xoff[j];
+                        if (v0) bf[j][0] = (uint32_t)xp[(size_t)k0 * plane] | ((uint32_t)xp[(size_t)(k0 + 1) * plane] << 16);
+                        if (v1) bf[j][1] = (uint32_t)xp[(size_t)(k0 + 8) * plane] | ((uint32_t)xp[(size_t)(k0 + 9) * plane] << 16);
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const int r0 = m * 16 + g, r1 = r0 + 8;
+                    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(wq + (size_t)r0 * p.Cin + k0);
+                    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(wq + (size_t)r1 * p.Cin + k0);
+                    uint32_t af[4];
+                    af[0] = (v0 && r0 < p.Cout) ? w0[0] : 0u;
+                    af[1] = (v0 && r1 < p.Cout) ? w1[0] : 0u;
+                    af[2] = (v1 && r0 < p.Cout) ? w0[4] : 0u;
+                    af[3] = (v1 && r1 < p.Cout) ? w1[4] : 0u;
+#pragma unroll
+                    for (int j = 0; j < NTP; ++j) mma_bf16_16816(acc[m][j], af, bf[j]);
+                }
+            }
+            // D fragment: rows g / g + 8 of the Cout tile, columns 2t, 2t + 1 of the pixel tile (neighbours in one patch row when pw is even)
+            __nv_bfloat16* ypatch = p.y + ((size_t)b * p.Cout * p.H + (size_t)pi * p.ph) * p.W + (size_t)jg * PGW + q * p.pw;
+#pragma unroll
+            for (int j = 0; j < NTP; ++j) {
+                const int pp = j * 8 + 2 * t;
+                if (pp >= npix) continue;
+                const int pr = pp / p.pw, pc = pp % p.pw, pr1 = (pp + 1) / p.pw, pc1 = (pp + 1) % p.pw;
+                const bool pair = (p.pw & 1) == 0;              // pixels pp, pp + 1 are neighbours in one patch row
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int oc = m * 16 + h * 8 + g;
+                        if (oc >= p.Cout) continue;
+                        const float a0 = act_apply(fmaf(acc[m][j][2 * h], sc[m][h], sh[m][h]), p.act);
+                        const float a1 = act_apply(fmaf(acc[m][j][2 * h + 1], sc[m][h], sh[m][h]), p.act);
+                        __nv_bfloat16* dst = ypatch + (size_t)oc * ostride + (size_t)pr * p.W + pc;
+                        if (pair) *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a0, a1);
+                        else {
+                            *dst = __float2bfloat16_rn(a0);
+                            if (pp + 1 < npix) ypatch[(size_t)oc * ostride + (size_t)pr1 * p.W + pc1] = __float2bfloat16_rn(a1);
+                        }
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_w + s * MMA_MAX_SLOTS + q);      // the weight row of this slot may be overwritten
+        }
+        __syncwarp();
+        if (lane == 0 && warp < users) mbar_arrive(empty_x + s);              // this warp is done with the unit's x tile
+    }
+}
+
+template <int MT, int NTP>
+static int launch_mma(const CUtensorMap& xmap, const RingParams& p, size_t smem, int grid, cudaStream_t st) {
+    auto k = conv1x1_mma_kernel<MT, NTP>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(HSB_ERR_CUDA, std::string("conv1x1_mma attr: ") + cudaGetErrorString(e));
+    k<<<grid, MMA_THREADS, smem, st>>>(xmap, p);
+    note_kernel("conv1x1_mma_kernel");
+    return check_launch("conv1x1_mma launch");
+}
+
 typedef CUresult (*EncodeTiledFnR)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -190,8 +363,62 @@ int conv1x1_ring_try(const void* x, const void* w, void* y, const float* post_sc
     // hide that better than one 256-thread CTA (measured at HyperSeg-M level 1 / 2: 12.6 / 10.5 us against 14.1 / 10.2 us
     // here; HSB_RING_ALL=1 forces this kernel for experiments).
     static const bool all = [] { const char* v = getenv("HSB_RING_ALL"); return v && v[0] == '1'; }();
-    if (ph * pw > 1 && !all) return HSB_OK;
     if (ph > 256 || ((uintptr_t)x & 15) || ((uintptr_t)w & 15) || ((uintptr_t)y & 3) || (W * 2) % 16 || (hp * 2) % 16 || (w_row_stride * 2) % 16) return HSB_OK;
+    EncodeTiledFnR encode = ring_encode_fn();
+    if (!encode) return HSB_OK;
+    const int wrow_e = ((Cin * Cout + 7) / 8 * 8) + ((((Cin * Cout + 7) / 8) % 2 == 0) ? 8 : 0);
+    const cuuint64_t dim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cin, (cuuint64_t)B};
+    const cuuint64_t str[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)Cin * H * W * 2};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    static const bool verbose = [] { const char* v = getenv("HSB_VERBOSE"); return v && v[0] == '1'; }();
+
+    // ---- tensor-core variant: patches of up to 16 pixels, up to 64 output channels.  Opt-in (HSB_CONV_MMA=1, read at every
+    // call so that tests can switch it): on B200 it measured 16.0 / 12.4 / 10.8 us at the three HyperSeg-M levels against
+    // 14.3 (CUDA-core ring) / 12.6 / 10.3 us (one-shot kernel) -- these launches are bound by launch + first-load latency, not
+    // by arithmetic or by the ring's granularity, so the simpler kernels stay the default. ----
+    const char* mma_env = getenv("HSB_CONV_MMA");
+    if (mma_env && mma_env[0] == '1' && !all && ph * pw <= 16 && Cout <= 64) {
+        // unit = PG patches, one per warp where possible: the smallest valid PG >= 8, else the largest valid one
+        int PG = 0;
+        for (int cand = 1; cand <= fw && cand <= MMA_MAX_SLOTS; ++cand) {
+            if (fw % cand || (cand * pw * 2) % 16 || cand * pw > 256) continue;
+            const size_t stage = (size_t)cand * wrow_e * 2 + (size_t)Cin * ph * cand * pw * 2 + 256;
+            if (2 * stage > 200 * 1024) break;
+            PG = cand;
+            if (cand >= 8) break;
+        }
+        if (PG) {
+            const int PGW = PG * pw, plane = ph * PGW;
+            RingParams p;
+            p.w = (const __nv_bfloat16*)w; p.y = (__nv_bfloat16*)y; p.post_scale = post_scale; p.post_shift = post_shift; p.act = act;
+            p.B = B; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.fh = fh; p.fw = fw; p.ph = ph; p.pw = pw;
+            p.PG = PG; p.upr = fw / PG; p.wsplit = 1; p.PGw = PG; p.units = B * fh * p.upr; p.hp = hp; p.w_row_stride = w_row_stride;
+            p.wrow = wrow_e;
+            p.x_off = (int)(((size_t)PG * p.wrow * 2 + 127) / 128 * 128);
+            p.stage_bytes = (int)(((size_t)p.x_off + (size_t)Cin * plane * 2 + 127) / 128 * 128);
+            p.stages = std::min(MMA_MAX_STAGES, (int)((220 * 1024) / p.stage_bytes));
+            p.lanes_over_pixels = 0;
+            const size_t smem = MMA_BAR_BYTES + (size_t)p.stages * p.stage_bytes;
+            CUtensorMap xmap;
+            const cuuint32_t box[4] = {(cuuint32_t)PGW, (cuuint32_t)ph, (cuuint32_t)Cin, 1};
+            if (p.stages >= 2 &&
+                encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dim, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                const int grid = std::min(p.units, std::max(1, device_sm_count()));
+                const int MT = (Cout + 15) / 16, NTP = (ph * pw + 7) / 8;
+                if (verbose)
+                    fprintf(stderr, "[hsb] conv1x1_mma: %d -> %d, %dx%d px/patch: %d patches per unit, %d units, %d Cout tiles x %d pixel tiles, %d stages of %d B\n",
+                            Cin, Cout, ph, pw, PG, p.units, MT, NTP, p.stages, p.stage_bytes);
+                *handled = true;
+#define HSB_MMA_CASE(M, N) if (MT == M && NTP == N) return launch_mma<M, N>(xmap, p, smem, grid, st);
+                HSB_MMA_CASE(1, 1) HSB_MMA_CASE(2, 1) HSB_MMA_CASE(3, 1) HSB_MMA_CASE(4, 1)
+                HSB_MMA_CASE(1, 2) HSB_MMA_CASE(2, 2) HSB_MMA_CASE(3, 2) HSB_MMA_CASE(4, 2)
+#undef HSB_MMA_CASE
+                *handled = false;
+            }
+        }
+    }
+    if (ph * pw > 1 && !all) return HSB_OK;
     // patches per unit: the x box must have 16-byte rows (PG * pw * 2 bytes) and PG must divide fw; the smallest such PG that
     // gives every thread an item (units stay small: more units than SMs, several stages in flight), else the largest one
     const int PB = (pw % 2 == 0) ? 2 : 1;
@@ -199,7 +426,6 @@ int conv1x1_ring_try(const void* x, const void* w, void* y, const float* post_sc
     static const int env_items = [] { const char* v = getenv("HSB_RING_ITEMS"); return v ? atoi(v) : 0; }();
     const int threads = env_threads >= 64 && env_threads <= RING_MAX_THREADS && env_threads % 32 == 0 ? env_threads : 256;
     const int min_items = env_items > 0 ? env_items : threads;
-    const int wrow_e = ((Cin * Cout + 7) / 8 * 8) + ((((Cin * Cout + 7) / 8) % 2 == 0) ? 8 : 0);
     // x box: the smallest PG with 16-byte rows.  Its patches are split over `wsplit` units (each loads the whole, small x box
     // and its own PGw weight rows): units stay small -- several per SM for balance, 3-4 stages in flight -- as long as a unit
     // still has an item for every thread with one output channel per thread.
@@ -226,18 +452,12 @@ int conv1x1_ring_try(const void* x, const void* w, void* y, const float* post_sc
     if (p.stages < 2) return HSB_OK;
     p.lanes_over_pixels = unit_pg >= 32;
     const size_t smem = 128 + (size_t)p.stages * p.stage_bytes;
-    EncodeTiledFnR encode = ring_encode_fn();
-    if (!encode) return HSB_OK;
     CUtensorMap xmap;
-    const cuuint64_t dim[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cin, (cuuint64_t)B};
-    const cuuint64_t str[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)Cin * H * W * 2};
     const cuuint32_t box[4] = {(cuuint32_t)PGW, (cuuint32_t)ph, (cuuint32_t)Cin, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
     if (encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dim, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return HSB_OK;
     const int grid = std::min(p.units, std::max(1, device_sm_count()));
-    static const bool verbose = [] { const char* v = getenv("HSB_VERBOSE"); return v && v[0] == '1'; }();
     if (verbose)
         fprintf(stderr, "[hsb] conv1x1_ring: %d -> %d, %dx%d px/patch: x box %d patches, %d weight rows per unit, %d units, OB %d PB %d, %d stages of %d B, %d threads\n",
                 Cin, Cout, ph, pw, PG, PGw, p.units, OB, PB, p.stages, p.stage_bytes, threads);

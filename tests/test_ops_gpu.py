@@ -585,14 +585,25 @@ def test_kernel_selection_is_observable():
     assert _lib.last_kernel() == "signal2weights_kernel"
 
 
-@pytest.mark.parametrize("geom", [(82, 64, 16, 32, 2), (130, 32, 24, 48, 1), (82, 64, 18, 24, 3), (20, 6, 5, 16, 2)])
-def test_conv1x1_ring_kernel_one_pixel_patches(geom):
-    """The persistent ring kernel (bf16, patch-major rows, one pixel per patch: the coarsest decoder level of every shipped
-    configuration) against the float64 oracle, with and without the fused BatchNorm + ReLU; patch counts that do not divide by
-    the SM count, a patch grid whose width is not a power of two, and the general kernel on the same data as a cross-check."""
+# (Cin, Cout, fh, fw, ph, pw, B): the 1x1 levels of the shipped configurations and shapes that exercise the masks
+RING_GEOMS = [(82, 64, 16, 32, 1, 1, 2), (94, 32, 16, 32, 2, 2, 2), (44, 16, 16, 32, 4, 4, 2),        # HyperSeg-M / CamVid levels 0-2
+              (130, 32, 24, 48, 1, 1, 1), (62, 16, 24, 48, 2, 2, 1), (26, 8, 12, 24, 4, 4, 1),        # HyperSeg-S Cityscapes
+              (82, 64, 18, 24, 1, 1, 3), (20, 6, 5, 16, 1, 1, 2), (30, 40, 3, 8, 3, 2, 2), (18, 24, 4, 16, 2, 1, 1)]
+
+
+@pytest.mark.parametrize("mma", [False, True])
+@pytest.mark.parametrize("geom", RING_GEOMS)
+def test_conv1x1_persistent_kernels(geom, mma, monkeypatch):
+    """The persistent TMA-ring kernels (bf16, patch-major rows) against the float64 oracle, with and without the fused
+    BatchNorm + ReLU: the default selection (ring kernel for one-pixel patches, one-shot kernel otherwise) and the opt-in
+    mma.sync variant (HSB_CONV_MMA=1) on every 1x1 level of the shipped configurations, output-channel counts that are not a
+    multiple of 16, Cin that is not a multiple of 16, odd patch widths, patch counts that do not divide by the SM count; the
+    general kernel on reference-layout weights as a cross-check."""
     from hyperseg_b200 import _lib
-    Cin, Cout, fh, fw, B = geom
-    x = _rand((B, Cin, fh, fw), 90).to(DEV, torch.bfloat16)
+    Cin, Cout, fh, fw, ph, pw, B = geom
+    monkeypatch.setenv("HSB_CONV_MMA", "1" if mma else "0")
+    want = "conv1x1_mma_kernel" if mma else ("conv1x1_ring_kernel" if ph * pw == 1 else "patch_conv1x1_kernel")
+    x = _rand((B, Cin, fh * ph, fw * pw), 90).to(DEV, torch.bfloat16)
     w = _rand((B, Cin * Cout, fh, fw), 91, 0.3).to(DEV, torch.bfloat16)
     scale, shift = _bn(Cout, 92)
     wl = ops.weights_to_patch_major(w)
@@ -600,7 +611,7 @@ def test_conv1x1_ring_kernel_one_pixel_patches(geom):
         args = (scale.to(DEV), shift.to(DEV), "relu") if fused else (None, None, "none")
         ref = orc.patch_conv1x1(x.float().cpu(), w.float().cpu(), Cout, 1, *((scale, shift, "relu") if fused else (None, None, "none")))
         y = ops.patch_conv1x1(x, wl, Cout, 1, *args)
-        assert _lib.last_kernel() == "conv1x1_ring_kernel", _lib.last_kernel()
+        assert _lib.last_kernel() == want, _lib.last_kernel()
         assert rel_err(y.float().cpu(), ref) < BF16_TOL
         y_general = ops.patch_conv1x1(x, w, Cout, 1, *args)                 # reference-layout weights: the one-shot kernel
         assert _lib.last_kernel() == "patch_conv1x1_kernel"
