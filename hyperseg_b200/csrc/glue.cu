@@ -250,6 +250,43 @@ __global__ void __launch_bounds__(256) decoder_prev2x_kernel(const DecInParams p
     }
 }
 
+// feature channels of the level input when the encoder hands them over channels-last (bf16): one thread = 8 pixels x 8
+// channels.  It reads eight 16-byte pixel rows (neighbouring lanes take the neighbouring channel groups of the same pixels, so a
+// warp consumes whole contiguous runs), transposes the 8 x 8 tile in registers and writes eight 16-byte channel rows.  The
+// generic kernel above reads one channel per thread: at 16 channels every 32-byte sector was fetched 16 times (70 us for the
+// last level of HyperSeg-M, as long as the fused MetaBlock that consumes it).
+__global__ void __launch_bounds__(256) decoder_feat_nhwc_kernel(const DecInParams p) {
+    const int segs = p.W / 8, cgs = p.Cf / 8;
+    const size_t total = (size_t)p.B * p.H * segs * cgs;
+    const __nv_bfloat16* feat = reinterpret_cast<const __nv_bfloat16*>(p.feat);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int cg = idx % cgs;
+        const int sg = (idx / cgs) % segs;
+        const int y = (idx / ((size_t)cgs * segs)) % p.H;
+        const int b = idx / ((size_t)cgs * segs * p.H);
+        const __nv_bfloat16* src = feat + (size_t)b * p.fsb + (size_t)y * p.fsy + (size_t)(sg * 8) * p.fsx + cg * 8;
+        uint4 in[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) in[e] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)e * p.fsx));
+        __nv_bfloat16* dst = out + (((size_t)b * p.out_channels + p.Cc + cg * 8) * p.H + y) * p.W + sg * 8;
+        const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            // channel c of pixels (2k, 2k + 1): low or high half of word c / 2 of both pixel rows
+            const uint32_t sel = (c & 1) ? 0x7632u : 0x5410u;
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t a = reinterpret_cast<const uint32_t*>(&in[2 * k])[c >> 1];
+                const uint32_t bq = reinterpret_cast<const uint32_t*>(&in[2 * k + 1])[c >> 1];
+                w[k] = __byte_perm(a, bq, sel);
+            }
+            *reinterpret_cast<uint4*>(dst + (size_t)c * plane) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
 }  // namespace hsb
 
 using namespace hsb;
@@ -285,7 +322,19 @@ extern "C" int hsb_decoder_input_fwd(const void* coords, const void* feature, co
         DecInParams q = p;
         q.Cp = 0;                       // copy channels only; the output keeps its full channel count via out_channels
         q.out_channels = Cc + Cf + Cp;
-        const size_t t1 = (size_t)B * (Cc + Cf) * H * ((W + 7) / 8);
+        // channels-last feature with whole 8-channel groups: transposing copy; the generic kernel then only writes the coords
+        const char* no_nhwc = getenv("HSB_NO_NHWC_GLUE");      // A/B switch for scripts/time_glue.py
+        const bool nhwc8 = !(no_nhwc && no_nhwc[0] == '1') && Cf > 0 && Cf % 8 == 0 && W % 8 == 0 && f_stride_c == 1 && f_stride_x % 8 == 0 && f_stride_y % 8 == 0 &&
+                           f_stride_b % 8 == 0 && ((uintptr_t)feature % 16) == 0;
+        if (nhwc8) {
+            const size_t tf = (size_t)B * H * (W / 8) * (Cf / 8);
+            decoder_feat_nhwc_kernel<<<(int)std::min<size_t>((tf + 255) / 256, cap), 256, 0, st>>>(q);
+            rc = check_launch("decoder_feat_nhwc launch");
+            if (rc != HSB_OK || Cc == 0) return rc;
+            q.Cf = 0;                   // coords only ...
+            q.out_channels = Cc + Cf + Cp;
+        }
+        const size_t t1 = (size_t)B * (q.Cc + q.Cf) * H * ((W + 7) / 8);
         decoder_input_kernel<__nv_bfloat16><<<(int)std::min<size_t>((t1 + 255) / 256, cap), 256, 0, st>>>(q);
         return check_launch("decoder_input launch");
     }

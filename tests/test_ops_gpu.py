@@ -293,7 +293,7 @@ def test_ir_tensor_core_many_patches_per_cta():
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("geom", [(2, 16, 16, 128, 256, 64, 128), (1, 3, 7, 37, 52, 19, 26), (2, 10, 0, 16, 32, 1, 1),
-                                  (1, 6, 5, 24, 40, 24, 40)])
+                                  (1, 6, 5, 24, 40, 24, 40), (3, 24, 8, 32, 64, 16, 32), (1, 40, 32, 16, 24, 8, 12)])
 def test_decoder_input_matches_interpolate_cat(geom, dtype):
     import torch.nn.functional as F
     B, Cf, Cp, H, W, h, w = geom
