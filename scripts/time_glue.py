@@ -23,3 +23,9 @@ for name, (cf, cp, H, W) in {"L4": (16, 16, 256, 512), "L3": (24, 16, 128, 256)}
         us = graph_time([lambda f=f, pv=pv: ops.decoder_input(coords, f, pv) for f, pv in sets])
         nbytes = 2 * B * H * W * (cf + (2 + cf + cp)) + 2 * B * cp * H * W // 4
         print(f"{name} level input ({'generic' if mode == '1' else 'NHWC transposing copy'}): {us:.1f} us  {nbytes / us * 1e-3:.0f} GB/s", flush=True)
+
+# label tail: 2x bilinear upsampling of the class logits fused with argmax (hsb_upsample_argmax_fwd)
+sets = [rnd((B, 19, 256, 512), 30 + k).to(DEV, torch.bfloat16) for k in range(3)]
+us = graph_time([lambda l=l: ops.upsample_argmax(l, (512, 1024)) for l in sets])
+nb = 2 * B * 19 * 256 * 512 + B * 512 * 1024
+print(f"label tail (19 x 256x512 -> 512x1024 labels): {us:.1f} us  {nb / us * 1e-3:.0f} GB/s", flush=True)
