@@ -142,7 +142,11 @@ int hsb_signal2weights_fwd(const void* s, const void* ws, void* w_out,
 
 /*
  * Tensor-core variant of the weight head for bf16 (tcgen05).  The static head weights are first packed, once,
- * into the UMMA operand layout (K zero-padded to a multiple of 16, output channels tiled by 256 per group):
+ * into the UMMA operand layout.  The packed buffer is opaque (16-byte aligned, caller-allocated): when the head's signal
+ * slice fits one CTA's shared memory it holds an item table followed by 128-column tiles of the reference-order row whose K
+ * is the union of the signal groups they read (the kernel keeps the slice resident); otherwise one 256-column tile per
+ * (group, tile) with K = sig_ch / groups padded to 16.  hsb_head_pack and hsb_signal2weights_packed_fwd agree on the choice
+ * (a function of sig_ch, out_ch, groups only).
  *   hsb_head_packed_elems  number of bf16 elements the packed buffer needs (-1 on bad dimensions)
  *   hsb_head_pack          ws (out_ch, sig_ch/G) of `dtype` -> packed; row_scale (fp32, out_ch entries, may be NULL)
  *                          multiplies each output channel's row, which lets an inference engine fold a BatchNorm

@@ -1,4 +1,13 @@
-echo "== unroll 4 (default)"; timeout 200 python scripts/time_glue.py 2>&1 | tail -1
-echo "== unroll 1"; HSB_LIBRARY=$PWD/hyperseg_b200/libhsb200_t1.so timeout 200 python scripts/time_glue.py 2>&1 | tail -1
-echo "== unroll 8"; HSB_LIBRARY=$PWD/hyperseg_b200/libhsb200_t8.so timeout 200 python scripts/time_glue.py 2>&1 | tail -1
-timeout 300 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k "argmax or decoder_input or engine" 2>&1 | tail -2
+mkdir -p gpurun_out
+N=${NGPU:-4}
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --config l-voc-train --steps 6 --warmup 3 > gpurun_out/r02_bench_l_voc_train_n$N.json 2> gpurun_out/r02_bench_l_voc_train_n$N.err
+tail -c 200 gpurun_out/r02_bench_l_voc_train_n$N.err
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --no-cpu-baseline --no-gpu-reference > gpurun_out/r02_bench_m_n$N.json 2> gpurun_out/r02_bench_m_n$N.err
+tail -c 200 gpurun_out/r02_bench_m_n$N.err
+for f in gpurun_out/r02_bench_*_n$N.json; do echo "== $f"; python - "$f" <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+for k in ("metric","n_gpus","value","ms_per_step","e2e","e2e_uint8_frames","whole_box"):
+    if k in d: print(k, d[k])
+PY
+done
