@@ -710,6 +710,9 @@ def run_train(args):
 
     props = torch.cuda.get_device_properties(local)
     sampler = ClockSampler(local, f"GPU-{props.uuid}" if getattr(props, "uuid", None) else None)
+    # DDP rebuilds its gradient buckets after the first iteration and the caching allocator keeps growing for a few more:
+    # at least five untimed steps (a 4-GPU run with three still had a 136 ms step inside the timed region, 107 ms after it)
+    args.warmup = max(args.warmup, 5)
     for i in range(args.warmup):
         step(frames[i % 4], labels[i % 4])
     barrier()
