@@ -101,7 +101,10 @@ struct IR2 {
 #ifndef HSB_IR_RPT
 #define HSB_IR_RPT 4
 #endif
-    static constexpr int WT = PS == 16 ? HSB_IR_WT : 2, STRIPS = PS / WT, RPT = PS == 16 ? HSB_IR_RPT : 4, RG = RPH / RPT, WPH = STRIPS / 2 * RG;
+#ifndef HSB_IR_RPT8
+#define HSB_IR_RPT8 4        // 8x8 patches: 2x4 pixels per thread on 4 warps; 2x2 on 8 warps measured 31.9 vs 30.9 us at level 3
+#endif
+    static constexpr int WT = PS == 16 ? HSB_IR_WT : 2, STRIPS = PS / WT, RPT = PS == 16 ? HSB_IR_RPT : HSB_IR_RPT8, RG = RPH / RPT, WPH = STRIPS / 2 * RG;
     static constexpr int DWMAIN = WPH * M2T, DWN = DWMAIN;
     static constexpr int W_PROD = W_DW + DWN, PRODN = 4;                         // halo / mirror-row warps
     static constexpr int W_MMA1 = W_PROD + PRODN, W_MMA2 = W_MMA1 + 1, W_LOAD = W_MMA2 + 1;
