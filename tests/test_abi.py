@@ -131,3 +131,59 @@ def test_packed_head_cache_is_tied_to_the_live_tensor_object():
         ops._cache_store(cache, ("k", i), a, i)
     assert all(ops._cache_lookup(cache, ("k", i), a) == i for i in range(70))
     assert key not in cache                                      # ... dead ones are pruned once the table grows
+
+
+# ---- host-side planning entry points: pure functions of the geometry, callable without a GPU -------------------------------------
+# (Cin, hid, Cout, patch) of the shipped inverted-residual levels and their arranged row lengths: B1 [ceil(Cin/8)][hid][8] |
+# W2T [9][hid] padded to 16 bytes | B2 [ceil(hid/8)][Cout][8]
+IR_ROWS = {(34, 68, 19, 16): 5 * 68 * 8 + 616 + 9 * 19 * 8, (26, 52, 19, 16): 4 * 52 * 8 + 472 + 7 * 19 * 8,
+           (22, 44, 12, 16): 3 * 44 * 8 + 400 + 6 * 12 * 8, (24, 48, 16, 8): 3 * 48 * 8 + 432 + 6 * 16 * 8,
+           (14, 28, 8, 8): 2 * 28 * 8 + 256 + 4 * 8 * 8}
+
+
+def test_arranged_row_layout_and_supported_shapes(lib):
+    for (cin, hid, cout, ps), row in IR_ROWS.items():
+        assert lib.hsb_ir_arranged_row_elems(cin, hid, cout) == row, (cin, hid, cout)
+        assert row % 8 == 0                                       # a row is a whole number of 16-byte units
+        assert lib.hsb_patch_ir_arranged_supported(cin, hid, cout, ps) == 1
+        assert lib.hsb_patch_ir_arranged_supported(cin, hid, cout, 24 - ps) == 0      # the other patch size is not instantiated
+    assert lib.hsb_patch_ir_arranged_supported(20, 40, 8, 16) == 0
+    assert lib.hsb_ir_arranged_row_elems(0, 4, 4) == -1
+
+
+# (sig_index, sig_ch, head outputs, groups, hp_offset, Cin, hid, Cout): HyperSeg-M levels 4 / 3, unify's shared head (S-Cityscapes)
+ARRANGED_PLANS = [(0, 320, 4216, 4, 0, 34, 68, 19), (0, 192, 2352, 16, 0, 24, 48, 16), (768, 512, 3680, 16, 868, 26, 52, 19),
+                  (768, 512, 3680, 16, 0, 14, 28, 8), (0, 128, 1896, 8, 0, 22, 44, 12), (4, 192, 2352, 16, 0, 24, 48, 16)]
+
+
+@pytest.mark.parametrize("geom", ARRANGED_PLANS)
+def test_arranged_head_plan_is_consistent(lib, geom):
+    """hsb_head_arranged_plan: enough 128-column tiles to cover the arranged row, K a multiple of 16 that holds at least one
+    group's signal channels, packed size = tiles x 128 x K; geometry errors are reported, not planned around."""
+    import ctypes
+    si, sc, och, g, off, cin, hid, cout = geom
+    elems, items, kmax = ctypes.c_int64(0), ctypes.c_int(0), ctypes.c_int(0)
+    rc = lib.hsb_head_arranged_plan(si, sc, och, g, off, cin, hid, cout, ctypes.byref(elems), ctypes.byref(items), ctypes.byref(kmax))
+    assert rc == 0, lib.hsb_last_error()
+    row = lib.hsb_ir_arranged_row_elems(cin, hid, cout)
+    assert items.value * 128 >= row and items.value <= 2 * (-(-row // 128))
+    assert kmax.value % 16 == 0 and kmax.value >= sc // g and kmax.value <= 256
+    assert elems.value == items.value * 128 * kmax.value
+    # the block's hyper-parameters must fit the head: one output too few is an error
+    hp = cin * hid + 9 * hid + hid * cout
+    short = (off + hp - 1) // g * g
+    assert lib.hsb_head_arranged_plan(si, sc, short, g, off, cin, hid, cout, None, None, None) != 0
+    assert lib.hsb_head_arranged_plan(si, sc + 1, och, g, off, cin, hid, cout, None, None, None) != 0      # sig_ch % groups
+
+
+@pytest.mark.parametrize("geom", [(416, 5248, 32), (224, 3008, 16), (128, 704, 8), (192, 2352, 16), (320, 4216, 4), (576, 4160, 32),
+                                  (2048, 4096, 2)])
+def test_packed_head_size(lib, geom):
+    """hsb_head_packed_elems: never smaller than the weights themselves padded to 16 signal channels per group; the last
+    geometry (1024 signal channels per group: the slice cannot stay resident in one CTA) takes the legacy layout."""
+    sc, och, g = geom
+    n = lib.hsb_head_packed_elems(sc, och, g)
+    spg = sc // g
+    assert n >= och * (-(-spg // 16) * 16)
+    assert n % 8 == 0
+    assert lib.hsb_head_packed_elems(sc + 1, och, g) == -1
