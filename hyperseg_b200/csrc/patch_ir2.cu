@@ -234,25 +234,35 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
     const uint32_t sm_base = smem_u32(sm);
 
     // ---------------- one-time setup ----------------
-    for (int i = tid; i < C::OFF_BAR / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    for (int s = 0; s < 2; ++s) {
-        // constant-one channel of A1: k-group KC1, channel row 0, every M-group a tile may read (row 0 of a group's 8 rows
-        // is not touched by the swizzle); BN1 shift: row k = 8 KC1 of B1
-        for (int i = tid; i < (C::LO_ROWS + C::GPT) * (C::ROWB / 4); i += C::THREADS)
-            *reinterpret_cast<uint32_t*>(sm + C::OFF_A1 + s * C::SZ_A1 + C::KC1 * C::A1_KGS + (i / (C::ROWB / 4)) * C::GRP + (i % (C::ROWB / 4)) * 4) = 0x3F803F80u;
-        for (int n = tid; n < C::HID; n += C::THREADS)
-            *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_W1 + s * C::SZ_W1 + C::KC1 * C::B1_LBO + n * 16) = __float2bfloat16_rn(p.shift[0][n]);
-        // BN3 shift: row k = ONE2 of B2; constant-one channel ONE2 of A2 when it lives in the non-swizzled tail (else the
-        // depthwise warps write it with every row, because the output staging tile reuses the swizzled part)
-        for (int n = tid; n < C::COUT; n += C::THREADS)
-            *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_W23 + s * C::SZ_W23 + C::SZ_W2T + C::KC2 * C::B2_LBO + n * 16) = __float2bfloat16_rn(p.shift[2][n]);
-        if (C::ONE2 >= 64)
-            for (int m = tid; m < 128; m += C::THREADS)
-                *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A2 + s * C::SZ_A2 + C::SZ_A2S + ((C::ONE2 - 64) / 8) * C::A2T_LBO + m * 16) = __float2bfloat16_rn(1.f);
-    }
-    for (int n = tid; n < C::HID; n += C::THREADS) reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_B2B)[n] = __float2bfloat16_rn(p.shift[1][n]);
-    if (tid == 0) {
+    // this CTA's run of patches: balanced split (run lengths differ by at most one; grid <= total, so no run is empty)
+    const int n0 = (int)((long long)blockIdx.x * p.total / (int)gridDim.x);
+    const int n1 = (int)((long long)(blockIdx.x + 1) * p.total / (int)gridDim.x);
+    PatchWalk pw;
+    pw.init(n0, p.fh, p.fw);
+    // the x tile of a patch into stage s, in two parts (rows [0, LO_ROWS) / the rest + B1)
+    auto issue_lo = [&](const PatchWalk& w, uint32_t s) {
+        unsigned char* a1 = sm + C::OFF_A1 + s * C::SZ_A1;
+        mbar_arrive_expect_tx(lo_full + s, C::KC1 * C::LO_ROWS * C::GRP);
+#pragma unroll
+        for (int kg = 0; kg < (C::LO_ROWS > 0 ? C::KC1 : 0); ++kg) {
+            const bool tail = (C::CIN % 8 != 0) && kg == C::KC1 - 1;
+            tma_load_5d(a1 + kg * C::A1_KGS, tail ? &maps.lo_tail : &maps.lo, w.pj * C::PS, 0, w.pi * C::PS - 1, tail ? 0 : kg, w.b, lo_full + s);
+        }
+    };
+    auto issue_hi = [&](const PatchWalk& w, uint32_t s) {
+        unsigned char* a1 = sm + C::OFF_A1 + s * C::SZ_A1;
+        mbar_arrive_expect_tx(hi_full + s, C::KC1 * C::HI_ROWS * C::GRP + C::SZ_B1);
+        if (C::HI_ROWS > 0) {
+#pragma unroll
+            for (int kg = 0; kg < C::KC1; ++kg) {
+                const bool tail = (C::CIN % 8 != 0) && kg == C::KC1 - 1;
+                tma_load_5d(a1 + kg * C::A1_KGS + C::LO_ROWS * C::GRP, tail ? &maps.hi_tail : &maps.hi, w.pj * C::PS, 0, w.pi * C::PS - 1 + C::LO_ROWS,
+                            tail ? 0 : kg, w.b, hi_full + s);
+            }
+        }
+        bulk_g2s(sm + C::OFF_W1 + s * C::SZ_W1, p.w + (size_t)w.patch * p.w_row_stride, C::SZ_B1, hi_full + s);
+    };
+    auto init_barriers = [&]() {
         for (int s = 0; s < 2; ++s) {
             mbar_init(lo_full + s, 1);
             mbar_init(hi_full + s, 1);
@@ -276,19 +286,56 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
         tma_prefetch_desc(&maps.hi);
         tma_prefetch_desc(&maps.hi_tail);
         tma_prefetch_desc(&maps.y);
+    };
+#ifdef HSB_IR_EARLY
+    // Experiment, OFF: stage 0 of A1 / W1 is cleared first and the barriers are initialised, so that the first tile can be
+    // requested while the rest of the set-up is still running (about 1 us of the 8.8 us fixed cost).  A single small launch is
+    // clean under compute-sanitizer and correct, but the whole-model tests failed with this build (cause not found before the
+    // GPU budget of the round ran out), so the default keeps the serial set-up.
+    for (int i = tid; i < C::SZ_A1 / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm + C::OFF_A1)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < C::SZ_W1 / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm + C::OFF_W1)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) init_barriers();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (warp == C::W_LOAD && n0 < n1 && elect_one()) {
+        issue_lo(pw, 0);
+        issue_hi(pw, 0);
     }
+    for (int i = tid; i < C::OFF_BAR / 16; i += C::THREADS) {
+        const int off = i * 16;
+        const bool first = (off >= C::OFF_A1 && off < C::OFF_A1 + C::SZ_A1) || (off >= C::OFF_W1 && off < C::OFF_W1 + C::SZ_W1);
+        if (!first) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+#else
+    for (int i = tid; i < C::OFF_BAR / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+#endif
+    for (int s = 0; s < 2; ++s) {
+        // constant-one channel of A1: k-group KC1, channel row 0, every M-group a tile may read (row 0 of a group's 8 rows
+        // is not touched by the swizzle); BN1 shift: row k = 8 KC1 of B1
+        for (int i = tid; i < (C::LO_ROWS + C::GPT) * (C::ROWB / 4); i += C::THREADS)
+            *reinterpret_cast<uint32_t*>(sm + C::OFF_A1 + s * C::SZ_A1 + C::KC1 * C::A1_KGS + (i / (C::ROWB / 4)) * C::GRP + (i % (C::ROWB / 4)) * 4) = 0x3F803F80u;
+        for (int n = tid; n < C::HID; n += C::THREADS)
+            *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_W1 + s * C::SZ_W1 + C::KC1 * C::B1_LBO + n * 16) = __float2bfloat16_rn(p.shift[0][n]);
+        // BN3 shift: row k = ONE2 of B2; constant-one channel ONE2 of A2 when it lives in the non-swizzled tail (else the
+        // depthwise warps write it with every row, because the output staging tile reuses the swizzled part)
+        for (int n = tid; n < C::COUT; n += C::THREADS)
+            *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_W23 + s * C::SZ_W23 + C::SZ_W2T + C::KC2 * C::B2_LBO + n * 16) = __float2bfloat16_rn(p.shift[2][n]);
+        if (C::ONE2 >= 64)
+            for (int m = tid; m < 128; m += C::THREADS)
+                *reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_A2 + s * C::SZ_A2 + C::SZ_A2S + ((C::ONE2 - 64) / 8) * C::A2T_LBO + m * 16) = __float2bfloat16_rn(1.f);
+    }
+    for (int n = tid; n < C::HID; n += C::THREADS) reinterpret_cast<__nv_bfloat16*>(sm + C::OFF_B2B)[n] = __float2bfloat16_rn(p.shift[1][n]);
+#ifndef HSB_IR_EARLY
+    if (tid == 0) init_barriers();
+#endif
     if (warp == C::W_MMA1) tmem_alloc(tmem_slot, C::TMEM_COLS);
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-
-    // this CTA's run of patches: balanced split (run lengths differ by at most one; grid <= total, so no run is empty)
-    const int n0 = (int)((long long)blockIdx.x * p.total / (int)gridDim.x);
-    const int n1 = (int)((long long)(blockIdx.x + 1) * p.total / (int)gridDim.x);
-    PatchWalk pw;
-    pw.init(n0, p.fh, p.fw);
 
     if (warp >= C::W_PROD && warp < C::W_PROD + C::PRODN) {
         // =============== halo warps: halo columns and mirror rows of the tile in A1[s] ===============
@@ -439,30 +486,14 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
         PROF_BEGIN();
         for (uint32_t it = 0; pw.patch < n1; pw.next(p.fh, p.fw), ++it) {
             const uint32_t s = it & 1, ph = (it >> 1) & 1;
-            unsigned char* a1 = sm + C::OFF_A1 + s * C::SZ_A1;
-            const int x0 = pw.pj * C::PS, y0 = pw.pi * C::PS - 1;
+#ifdef HSB_IR_EARLY
+            if (it == 0) continue;                          // the first tile was requested during the set-up
+#endif
             PWAIT(0, lo_empty + s, ph ^ 1);
-            if (elect_one()) {
-                mbar_arrive_expect_tx(lo_full + s, C::KC1 * C::LO_ROWS * C::GRP);
-#pragma unroll
-                for (int kg = 0; kg < (C::LO_ROWS > 0 ? C::KC1 : 0); ++kg) {
-                    const bool tail = (C::CIN % 8 != 0) && kg == C::KC1 - 1;
-                    tma_load_5d(a1 + kg * C::A1_KGS, tail ? &maps.lo_tail : &maps.lo, x0, 0, y0, tail ? 0 : kg, pw.b, lo_full + s);
-                }
-            }
+            if (elect_one()) issue_lo(pw, s);
             __syncwarp();
             PWAIT(1, hi_empty + s, ph ^ 1);
-            if (elect_one()) {
-                mbar_arrive_expect_tx(hi_full + s, C::KC1 * C::HI_ROWS * C::GRP + C::SZ_B1);
-                if (C::HI_ROWS > 0) {
-#pragma unroll
-                    for (int kg = 0; kg < C::KC1; ++kg) {
-                        const bool tail = (C::CIN % 8 != 0) && kg == C::KC1 - 1;
-                        tma_load_5d(a1 + kg * C::A1_KGS + C::LO_ROWS * C::GRP, tail ? &maps.hi_tail : &maps.hi, x0, 0, y0 + C::LO_ROWS, tail ? 0 : kg, pw.b, hi_full + s);
-                    }
-                }
-                bulk_g2s(sm + C::OFF_W1 + s * C::SZ_W1, p.w + (size_t)pw.patch * p.w_row_stride, C::SZ_B1, hi_full + s);
-            }
+            if (elect_one()) issue_hi(pw, s);
             __syncwarp();
         }
         PROF_END(7, lane == 0);
