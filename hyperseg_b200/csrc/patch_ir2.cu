@@ -290,8 +290,10 @@ patch_ir2_kernel(const __grid_constant__ IR2Maps maps, const IR2Params p) {
 #ifdef HSB_IR_EARLY
     // Experiment, OFF: stage 0 of A1 / W1 is cleared first and the barriers are initialised, so that the first tile can be
     // requested while the rest of the set-up is still running (about 1 us of the 8.8 us fixed cost).  A single small launch is
-    // clean under compute-sanitizer and correct, but the whole-model tests failed with this build (cause not found before the
-    // GPU budget of the round ran out), so the default keeps the serial set-up.
+    // clean under compute-sanitizer and correct, and so are 8x8-patch shapes with several patches per CTA, but 16x16-patch
+    // shapes with several patches per CTA come out wrong (rel. error 0.16 against the round-1 kernel, no memory error;
+    // scripts/ir2_tiny.py) -- the first patch of a run whose halo columns come from its neighbours.  Cause not found before
+    // the GPU budget of the round ran out, so the default keeps the serial set-up.
     for (int i = tid; i < C::SZ_A1 / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm + C::OFF_A1)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < C::SZ_W1 / 16; i += C::THREADS) reinterpret_cast<uint4*>(sm + C::OFF_W1)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) init_barriers();
